@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- FASTQ GB/s (delimit + per-position base/quality histograms) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic 150 bp FASTQ (SURVEY.md 8(d),
+input A): newline / record-boundary scan with '@'/'+' validation, the line-end index, and the
+per-position ACGTN + quality-byte histograms, fused in one sm_100a kernel.
+
+  value     whole-job GB/s with the bytes already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the host API (fqb_parse_host): pinned host bytes -> H2D -> kernels
+            -> D2H of the outcome + stats block, every step
+  roofline  the scan kernel against the measured HBM bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the CPU oracle's parallel_each (C restatement of
+            src/lib.rs:509-566; the Rust crate cannot be built here) on the box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 150
+REC_BYTES = 17 + 2 * (READ_LEN + 1) + 2  # 321
+GIB = 1 << 30
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_host_sample(n_bytes: int, threads: int) -> np.ndarray:
+    """Synthetic input A on the host with the oracle's generator (threads: ctypes drops the GIL)."""
+    from oracle import oracle
+    n_bytes = n_bytes // REC_BYTES * REC_BYTES
+    out = np.empty(n_bytes, dtype=np.uint8)
+    L = oracle.lib()
+    nrec = n_bytes // REC_BYTES
+    per = (nrec + threads - 1) // threads
+
+    def work(k):
+        a, b = k * per * REC_BYTES, min(nrec, (k + 1) * per) * REC_BYTES
+        if b > a:
+            L.fqo_synth_fixed(oracle.SEED, READ_LEN, a, b - a, out.ctypes.data + a)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+def cpu_parallel_each(sample: np.ndarray, workers: int, reps: int = 1):
+    """The reference's CPU path (parallel_each + stats closure) via the oracle; GB/s."""
+    from oracle import oracle
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc, st, _ = oracle.parallel_each_stats(sample, READ_LEN, workers)
+        dt = time.perf_counter() - t0
+        assert rc == 0 and st.n_records == sample.size // REC_BYTES
+        best = dt if best is None else min(best, dt)
+    return sample.size / best / 1e9
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    workers = max(1, cores - 1)          # + the serial producer thread (src/lib.rs:535)
+    sample_bytes = int(args.cpu_sample_gib * GIB)
+    sample = gen_host_sample(sample_bytes, cores)
+    for _ in range(args.warmup):
+        cpu_parallel_each(sample[: min(sample.size, 64 << 20) // REC_BYTES * REC_BYTES], workers)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_parallel_each(sample, workers)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample.size / dt / 1e9
+    desc = f"{sample.size / GIB:.2f} GiB prefix of the synthetic 150 bp stream per step, in host RAM"
+    line = {
+        "impl": "reference", "metric": "fastq_delimit_hist_GBps", "value": v, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": workers + 1, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU oracle = C restatement of fastq-rs parallel_each (serial delimiting + N stats workers); "
+                "the Rust crate cannot be built in this image",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"{args.gib:g} GiB/GPU in-HBM synthetic 150 bp fixed-length FASTQ: delimit + line-end index "
+                        "+ per-position ACGTN and quality histograms (BASELINE configs[1]+[2], one fused pass)",
+            "read_len": READ_LEN, "record_bytes": REC_BYTES, "bytes_per_gpu": int(args.gib * GIB),
+            "sharding": f"byte-chunk x{n_gpus}" if n_gpus > 1 else "none",
+            "l2": "inputs (GiBs) far larger than the 126 MB L2; no flush needed"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fastq_rs_b200 as fq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    eng = fq.Engine(max_len=READ_LEN, device=local, slot_bytes=args.slot_mib << 20, n_slots=3)
+
+    # ---- the stream: world x gib GiB of synthetic input A, sharded by byte chunk ------------
+    shard = int(args.gib * GIB) // 16 * 16
+    total = world * shard // REC_BYTES * REC_BYTES          # whole records overall
+    a, b = rank * shard, min(total, (rank + 1) * shard)
+    halo = min(total - b, fq._lib.MAX_RECORD_BYTES)
+    n_own, n_avail = b - a, b - a + halo
+    buf = torch.empty(16 + n_avail + 64, dtype=torch.uint8, device=dev)
+    front = 16 if a > 0 else 0
+    eng.synth_fixed(buf.data_ptr() + 16 - front, n_avail + front, byte_off=a - front, read_len=READ_LEN)
+    data = buf[16:]
+    n_rec_upper = n_avail // REC_BYTES + 2
+    index = torch.empty(4 * n_rec_upper, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    stats_dev = eng.device_stats()
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        """One pass of the hot path over this rank's shard (+ the exchange steps when sharded)."""
+        line_base = 0
+        if world > 1:
+            # line phase: '\n' count of every shard (8 bytes per rank), prefix = lines before mine
+            mine = torch.tensor([eng.count_lines(data, n_own)], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts, mine)
+            line_base = int(counts[:rank].sum().item())
+        eng.parse_device(data, n_own=n_own, n_avail=n_avail, hist=True, index=index, line_base=line_base,
+                         stream_offset=a, line_start=(a == 0), front16=(a > 0), eof=(b + halo == total))
+        if world > 1:
+            dist.all_reduce(stats_dev, op=dist.ReduceOp.SUM)   # the one collective on the data path
+        return eng.fetch()
+
+    for _ in range(args.warmup):
+        out, st = step()
+    assert out.status == 0, out
+    assert st.n_records == total // REC_BYTES, (st.n_records, total // REC_BYTES)
+    assert int(st.qual_hist.sum()) == READ_LEN * st.n_records
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: HBM-resident ---------------------------------------------------------
+    launches0 = eng.launch_count()
+    scan_ms = []
+    with ClockSampler(local) as clk:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            scan_ms.append(eng.last_scan_ms())
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = total / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (fq_scan_kernel), live CUDA events on its stream -----
+    peak, peak_src = peaks()
+    k_ms = float(np.mean(scan_ms))
+    alg_bytes = n_own + 16 * (n_own // REC_BYTES)            # 1 B read per input byte + 16 B index per record
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "fq_scan_kernel<5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": args.traffic_bytes, "peak_source": peak_src,
+                "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes}
+
+    # ---- end to end through the host API (rank-local; pinned host bytes) ---------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, eng, data, n_own if world == 1 else n_own // REC_BYTES * REC_BYTES, world, dev, a)
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "fastq_delimit_hist_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world), "roofline": roofline, "clocks": clk.summary(),
+            "gpu_launches": int(launches), "records": total // REC_BYTES,
+        }
+    if e2e is not None:
+        ev = torch.tensor([e2e["bytes"], e2e["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            tot_b = ev[0:1].clone()
+            mx_s = ev[1:2].clone()
+            dist.all_reduce(tot_b, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx_s, op=dist.ReduceOp.MAX)
+            ev = torch.cat([tot_b, mx_s])
+        if rank == 0:
+            line["e2e"] = {"value": float(ev[0].item()) / float(ev[1].item()) / 1e9, "unit": "GB/s",
+                           "h2d_bytes_per_step": int(e2e["bytes"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                           "bytes_per_gpu": int(e2e["bytes"]), "api": "fqb_parse_host (pinned ring, 3 slots)"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        workers = max(1, cores - 1)
+        sample = gen_host_sample(int(args.cpu_sample_gib * GIB), cores)
+        v = cpu_parallel_each(sample, workers, reps=2)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "GB/s", "cores": workers + 1, "kind": "port",
+            "sample": f"{sample.size / GIB:.2f} GiB prefix of the same synthetic stream, host RAM, best of 2; "
+                      f"oracle parallel_each({workers}) + stats closure"}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, eng, data, n, world, dev, stream_off):
+    """fqb_parse_host on pinned host memory holding this rank's bytes (whole records)."""
+    import torch
+    from fastq_rs_b200 import _lib
+    L = _lib.lib()
+    n = min(n, int(args.e2e_gib * GIB)) // REC_BYTES * REC_BYTES
+    # this rank's shard may start mid-record: skip to its first record start so the host stream is a valid file
+    skip = (-stream_off) % REC_BYTES
+    n = min(n, (data.numel() - skip)) // REC_BYTES * REC_BYTES
+    p = ctypes.c_void_p()
+    while n > 0 and L.fqb_host_alloc(n, ctypes.byref(p)) != 0:
+        n = n // 2 // REC_BYTES * REC_BYTES
+    if n <= 0:
+        return None
+    host = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(n,))
+    torch.from_numpy(host).copy_(data[skip:skip + n])
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, args.e2e_steps))
+    out, st, _ = eng.parse_host((p.value, n))            # warm-up (allocates the ring)
+    assert out.status == 0 and out.n_records == n // REC_BYTES, out
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out, st, _ = eng.parse_host((p.value, n))
+    dt = (time.perf_counter() - t0) / steps
+    assert out.n_records == n // REC_BYTES
+    L.fqb_host_free(p)
+    return {"bytes": n, "seconds": dt, "d2h": eng.n_words * 8 + 64}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gib", type=float, default=16.0, help="GiB of FASTQ per GPU")
+    ap.add_argument("--e2e-gib", type=float, default=16.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--slot-mib", type=int, default=64)
+    ap.add_argument("--cpu-sample-gib", type=float, default=2.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes/launch from the committed ncu --set full capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

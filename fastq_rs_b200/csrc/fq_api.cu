@@ -1,0 +1,649 @@
+// fq_api.cu -- the C ABI (include/fastq_b200.h) over the sm_100a kernels.
+//
+// Host-side counterpart of the reference's drivers:
+//   Parser::new / each            src/lib.rs:198-238   -> fqb_create / fqb_parse_device / fqb_parse_host
+//   Buffer (sliding window)       src/buffer.rs:3-112  -> contiguous device ring: a record is owned by
+//                                                        the chunk it starts in and read through into the next
+//   thread_reader (2-queue ring)  src/thread_reader.rs:8-200 -> pinned slots: acquire / submit / recycle on event
+#include "../../include/fastq_b200.h"
+#include "fq_common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace fq;
+
+namespace {
+
+__global__ void fq_init_kernel(DevResult* r, unsigned int* ticket)
+{
+    r->first_bad = NONE64;
+    r->tail_start = NONE64;
+    r->n_lines = 0;
+    r->line_end = 0;
+    r->err_offset = 0;
+    r->n_records = 0;
+    r->status = 0;
+    r->finished = 0;
+    *ticket = 0;
+}
+
+struct Slot {  // one stage of the streaming ring
+    uint8_t* h_pinned = nullptr;
+    cudaEvent_t copied = nullptr;  // H2D of the chunk in this host slot finished
+    bool copied_pending = false;
+};
+
+struct DevSlot {
+    cudaEvent_t done = nullptr;  // kernels that read this device slot finished
+    bool done_pending = false;
+    uint32_t* d_index = nullptr;
+    uint64_t bytes = 0;
+};
+
+}  // namespace
+
+struct fqb_ctx {
+    int device = 0;
+    uint32_t P = 0;
+    int nchunk = 5;
+    int num_sms = 148;
+    int grid = 148;
+    size_t nwords = 0;
+    // one-shot / per-chunk device state
+    uint64_t* d_stats = nullptr;
+    uint64_t* d_seqraw = nullptr;
+    DevResult* d_res = nullptr;
+    unsigned int* d_ticket = nullptr;
+    uint64_t* d_status = nullptr;
+    size_t status_cap = 0;
+    unsigned long long* d_linecount = nullptr;
+    DevResult* h_res = nullptr;  // pinned
+    unsigned long long* h_linecount = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    uint64_t launches = 0;
+    uint64_t last_off = 0;
+    std::string err;
+    // streaming
+    uint64_t slot_bytes = 0;
+    uint32_t n_slots = 0;
+    std::vector<Slot> slots;
+    std::vector<DevSlot> dslots;
+    uint8_t* d_ring = nullptr;  // n_dev * slot_bytes + halo
+    uint32_t n_dev = 0;
+    uint64_t* d_total = nullptr;
+    DevCarry* d_carry = nullptr;
+    DevCarry* h_carry = nullptr;  // pinned
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    bool streaming = false;
+    uint32_t stream_flags = 0;
+    uint64_t chunk_no = 0;       // chunks submitted to the device
+    uint64_t fill = 0;           // bytes filled in the current host slot
+    uint64_t stream_pos = 0;     // stream offset of the current host slot's first byte
+    bool acquired = false;
+    bool have_pending = false;   // a copied chunk is waiting for its successor (or EOF)
+    uint64_t pending_bytes = 0, pending_chunk = 0, pending_off = 0;
+    bool pending_line_start = true;  // the byte before the pending chunk is '\n' (or stream start)
+    bool last_byte_nl = true;        // last byte copied so far is '\n' (true before the first byte)
+    // host index collection (generic closure path)
+    uint32_t* host_index = nullptr;
+    uint64_t host_index_cap = 0, host_index_n = 0;
+};
+
+static int fail(fqb_ctx* c, cudaError_t e, const char* what)
+{
+    if (c) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        c->err = buf;
+    }
+    return FQB_E_CUDA;
+}
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return fail(ctx, e_, #call); \
+    } while (0)
+
+extern "C" {
+
+uint32_t fqb_abi_version(void) { return FQB_ABI_VERSION; }
+size_t fqb_stats_words(uint32_t P) { return stats_words(P); }
+size_t fqb_stats_len_hist_off(uint32_t P) { return stats_len_off(P); }
+size_t fqb_stats_base_hist_off(uint32_t P) { return stats_base_off(P); }
+size_t fqb_stats_qual_hist_off(uint32_t P) { return stats_qual_off(P); }
+
+const char* fqb_strerror(int status)
+{
+    switch (status) {
+    case FQB_OK: return "ok";
+    case FQB_E_HEADER: return "Fastq headers must start with '@'";
+    case FQB_E_SEP: return "Sequence and quality not separated by +";
+    case FQB_E_LENGTH: return "Sequence and quality length mismatch";
+    case FQB_E_TOO_LONG: return "Fastq record is too long";
+    case FQB_E_TRUNCATED: return "Possibly truncated input file";
+    case FQB_E_IO: return "I/O error";
+    case FQB_E_ARG: return "invalid argument";
+    case FQB_E_STATE: return "call out of order";
+    case FQB_E_NOMEM: return "out of memory";
+    case FQB_E_CUDA: return "CUDA error";
+    default: return "unknown status";
+    }
+}
+
+const char* fqb_last_error(fqb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fqb_create(const fqb_config* cfg, fqb_ctx** out)
+{
+    if (!cfg || !out || cfg->abi_version != FQB_ABI_VERSION || cfg->max_len == 0 || cfg->max_len > 4096)
+        return FQB_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FQB_E_CUDA;  // no CPU fallback, by design
+    if (cfg->device < 0 || cfg->device >= ndev) return FQB_E_ARG;
+    fqb_ctx* ctx = new fqb_ctx();
+    ctx->device = cfg->device;
+    ctx->P = cfg->max_len;
+    ctx->nchunk = cfg->max_len <= 160 ? 5 : 10;
+    ctx->nwords = stats_words(ctx->P);
+    ctx->slot_bytes = cfg->slot_bytes ? (cfg->slot_bytes + 4095) / 4096 * 4096 : (64ull << 20);
+    if (ctx->slot_bytes < 2 * (uint64_t)MAXREC) ctx->slot_bytes = 2 * (uint64_t)MAXREC;
+    ctx->n_slots = cfg->n_slots ? cfg->n_slots : 3;
+    if (ctx->n_slots < 2) ctx->n_slots = 2;
+    cudaError_t e;
+#define CKC(call)                        \
+    if ((e = (call)) != cudaSuccess) {   \
+        fail(ctx, e, #call);             \
+        fprintf(stderr, "fastq_b200: %s\n", ctx->err.c_str()); \
+        fqb_destroy(ctx);                \
+        return FQB_E_CUDA;               \
+    }
+    CKC(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CKC(scan_configure());
+    ctx->grid = ctx->num_sms * scan_blocks_per_sm(ctx->nchunk);
+    CKC(cudaMalloc(&ctx->d_stats, ctx->nwords * 8));
+    CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
+    CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
+    CKC(cudaMalloc(&ctx->d_ticket, 16));
+    CKC(cudaMalloc(&ctx->d_linecount, 8));
+    CKC(cudaMalloc(&ctx->d_carry, sizeof(DevCarry)));
+    CKC(cudaHostAlloc(&ctx->h_res, sizeof(DevResult), cudaHostAllocDefault));
+    CKC(cudaHostAlloc(&ctx->h_linecount, 8, cudaHostAllocDefault));
+    CKC(cudaHostAlloc(&ctx->h_carry, sizeof(DevCarry), cudaHostAllocDefault));
+    CKC(cudaEventCreate(&ctx->ev0));
+    CKC(cudaEventCreate(&ctx->ev1));
+#undef CKC
+    *out = ctx;
+    return FQB_OK;
+}
+
+static void stream_free(fqb_ctx* ctx)
+{
+    for (auto& s : ctx->slots) {
+        if (s.h_pinned) cudaFreeHost(s.h_pinned);
+        if (s.copied) cudaEventDestroy(s.copied);
+    }
+    ctx->slots.clear();
+    for (auto& d : ctx->dslots) {
+        if (d.done) cudaEventDestroy(d.done);
+        if (d.d_index) cudaFree(d.d_index);
+    }
+    ctx->dslots.clear();
+    if (ctx->d_ring) cudaFree(ctx->d_ring);
+    ctx->d_ring = nullptr;
+    if (ctx->d_total) cudaFree(ctx->d_total);
+    ctx->d_total = nullptr;
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    ctx->s_copy = ctx->s_comp = nullptr;
+}
+
+void fqb_destroy(fqb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    stream_free(ctx);
+    cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_seqraw);
+    cudaFree(ctx->d_res);
+    cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_status);
+    cudaFree(ctx->d_linecount);
+    cudaFree(ctx->d_carry);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->h_linecount) cudaFreeHost(ctx->h_linecount);
+    if (ctx->h_carry) cudaFreeHost(ctx->h_carry);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+// Enqueue the whole parse of one shard on `st`:
+//   reset -> scan (K1+K2) -> diagnose -> [reset + scan again, restricted to records before the
+//   first bad one: each() delivers exactly those, src/lib.rs:226-237] -> finalize
+static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, DevCarry* carry, uint64_t* total,
+                         bool timed)
+{
+    if (!sh || sh->n_avail < sh->n_own) return FQB_E_ARG;
+    if (sh->n_avail && (!sh->d_bytes || (reinterpret_cast<uintptr_t>(sh->d_bytes) & 15))) return FQB_E_ARG;
+    if ((sh->flags & FQB_F_INDEX) && sh->index_cap && !sh->d_index) return FQB_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t ntiles64 = (sh->n_own + TILE - 1) / TILE;
+    if (ntiles64 > 0xFFFFFFF0ull) return FQB_E_ARG;
+    if (ntiles64 > ctx->status_cap) {
+        if (ctx->d_status) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(ctx->d_status));
+            ctx->d_status = nullptr;
+        }
+        size_t cap = std::max<size_t>(ntiles64, 4096);
+        CK(cudaMalloc(&ctx->d_status, cap * 8));
+        ctx->status_cap = cap;
+    }
+    ScanParams p;
+    memset(&p, 0, sizeof p);
+    p.data = sh->d_bytes;
+    p.n_own = sh->n_own;
+    p.n_avail = sh->n_avail;
+    p.stream_offset = sh->stream_offset;
+    p.line_base = sh->line_base;
+    p.carry = carry;
+    p.flags = (sh->flags & (F_HIST | F_INDEX | F_LINE_START | F_EOF | F_FRONT16)) | (carry ? F_CARRY : 0);
+    if ((p.flags & F_FRONT16) && (p.flags & F_LINE_START)) return FQB_E_ARG;
+    p.max_len = ctx->P;
+    p.ntiles = (uint32_t)ntiles64;
+    p.tile_status = reinterpret_cast<unsigned long long*>(ctx->d_status);
+    p.ticket = ctx->d_ticket;
+    p.index = sh->d_index;
+    p.index_cap = sh->index_cap;
+    p.res = ctx->d_res;
+    p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
+    p.seqraw = reinterpret_cast<unsigned long long*>(ctx->d_seqraw);
+
+    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, ctx->d_ticket);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
+    CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
+    if (p.ntiles) CK(cudaMemsetAsync(ctx->d_status, 0, (size_t)p.ntiles * 8, st));
+    ctx->launches += 1;
+    if (p.ntiles) {
+        if (timed) CK(cudaEventRecord(ctx->ev0, st));
+        CK(launch_scan(p, ctx->nchunk, ctx->grid, st));
+        if (timed) {
+            CK(cudaEventRecord(ctx->ev1, st));
+            ctx->ev_valid = true;
+        }
+        CK(launch_diagnose(p, carry, st));
+        CK(launch_rerun_reset(p, st));
+        ScanParams p2 = p;
+        p2.flags |= F_RERUN;
+        CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
+        ctx->launches += 4;
+    }
+    CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), st));
+    ctx->launches += 1;
+    return FQB_OK;
+}
+
+int fqb_parse_device(fqb_ctx* ctx, const fqb_shard* shard, void* stream)
+{
+    if (!ctx || !shard) return FQB_E_ARG;
+    ctx->last_off = shard->stream_offset;
+    return enqueue_parse(ctx, shard, static_cast<cudaStream_t>(stream), nullptr, nullptr, true);
+}
+
+static void fill_result(const DevResult* r, uint64_t stream_offset_of_tail_base, fqb_result* res)
+{
+    res->status = r->status;
+    res->finished = r->finished;
+    res->n_records = r->n_records;
+    res->n_lines = r->n_lines;
+    res->err_offset = r->err_offset;
+    res->tail_offset = r->tail_start == NONE64 ? UINT64_MAX : stream_offset_of_tail_base + r->tail_start;
+}
+
+int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
+{
+    if (!ctx || !res) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, st));
+    if (host_stats) CK(cudaMemcpyAsync(host_stats, ctx->d_stats, ctx->nwords * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    fill_result(ctx->h_res, ctx->last_off, res);
+    return FQB_OK;
+}
+
+uint64_t* fqb_device_stats(fqb_ctx* ctx) { return ctx ? ctx->d_stats : nullptr; }
+uint64_t fqb_launch_count(fqb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float fqb_last_scan_ms(fqb_ctx* ctx)
+{
+    if (!ctx || !ctx->ev_valid) return -1.f;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int fqb_count_lines_device(fqb_ctx* ctx, const uint8_t* d_bytes, uint64_t n, void* stream)
+{
+    if (!ctx || (n && (!d_bytes || (reinterpret_cast<uintptr_t>(d_bytes) & 15)))) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_linecount, 0, 8, st));
+    if (n) {
+        CK(launch_count(d_bytes, n, ctx->d_linecount, ctx->num_sms * 8, st));
+        ctx->launches += 1;
+    }
+    return FQB_OK;
+}
+
+int fqb_fetch_line_count(fqb_ctx* ctx, void* stream, uint64_t* n_lines)
+{
+    if (!ctx || !n_lines) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(ctx->h_linecount, ctx->d_linecount, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_lines = *ctx->h_linecount;
+    return FQB_OK;
+}
+
+int fqb_host_alloc(uint64_t bytes, void** out)
+{
+    if (!out) return FQB_E_ARG;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return FQB_E_NOMEM;
+    }
+    *out = p;
+    return FQB_OK;
+}
+
+void fqb_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int fqb_synth_fixed_device(uint8_t* d_out, uint64_t n, uint64_t byte_off, uint32_t L, uint64_t seed, void* stream)
+{
+    if ((n && !d_out) || L == 0 || L > 1023) return FQB_E_ARG;
+    return launch_synth_fixed(d_out, n, byte_off, L, seed, static_cast<cudaStream_t>(stream)) == cudaSuccess ? FQB_OK
+                                                                                                             : FQB_E_CUDA;
+}
+
+int fqb_synth_var_device(uint8_t* d_out, const uint64_t* d_rec_off, uint64_t first, uint64_t count, uint64_t seed,
+                         void* stream)
+{
+    if (count && (!d_out || !d_rec_off)) return FQB_E_ARG;
+    return launch_synth_var(d_out, reinterpret_cast<const unsigned long long*>(d_rec_off), first, count, seed,
+                            static_cast<cudaStream_t>(stream)) == cudaSuccess
+               ? FQB_OK
+               : FQB_E_CUDA;
+}
+
+int fqb_synth_var_sizes_device(uint64_t* d_sizes, uint64_t first, uint64_t count, uint64_t seed, void* stream)
+{
+    if (count && !d_sizes) return FQB_E_ARG;
+    return launch_synth_var_sizes(reinterpret_cast<unsigned long long*>(d_sizes), first, count, seed,
+                                  static_cast<cudaStream_t>(stream)) == cudaSuccess
+               ? FQB_OK
+               : FQB_E_CUDA;
+}
+
+// ==========================================================================================
+// streaming ring
+// ==========================================================================================
+// Device ring: n_dev slots of slot_bytes laid out back to back, plus MAXREC bytes behind the last
+// slot that mirror the head of slot 0, so that every chunk is followed in memory by the head of
+// its successor.  Chunk i is parsed once chunk i+1 has landed (or EOF is known): records are
+// owned by the chunk they start in and are read through into the next one -- no partial-record
+// memmove as in Buffer::clean (src/buffer.rs:51-72), no host round trip between chunks.
+
+static int stream_alloc(fqb_ctx* ctx)
+{
+    if (ctx->d_ring) return FQB_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_dev = ctx->n_slots + 1;
+    CK(cudaMalloc(&ctx->d_ring, (size_t)ctx->n_dev * ctx->slot_bytes + MAXREC + 64));
+    CK(cudaMalloc(&ctx->d_total, ctx->nwords * 8));
+    CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    ctx->slots.resize(ctx->n_slots);
+    for (auto& s : ctx->slots) {
+        CK(cudaHostAlloc(&s.h_pinned, ctx->slot_bytes, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    }
+    ctx->dslots.resize(ctx->n_dev);
+    for (auto& d : ctx->dslots) CK(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
+    return FQB_OK;
+}
+
+int fqb_stream_begin(fqb_ctx* ctx, uint32_t flags)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (ctx->streaming) return FQB_E_STATE;
+    int rc = stream_alloc(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_total, 0, ctx->nwords * 8, ctx->s_comp));
+    CK(cudaMemsetAsync(ctx->d_carry, 0, sizeof(DevCarry), ctx->s_comp));
+    ctx->streaming = true;
+    ctx->stream_flags = flags & (FQB_F_HIST | FQB_F_INDEX);
+    ctx->chunk_no = 0;
+    ctx->fill = 0;
+    ctx->stream_pos = 0;
+    ctx->acquired = false;
+    ctx->have_pending = false;
+    ctx->last_byte_nl = true;
+    ctx->host_index_n = 0;
+    for (auto& s : ctx->slots) s.copied_pending = false;
+    for (auto& d : ctx->dslots) d.done_pending = false;
+    return FQB_OK;
+}
+
+// launch the parse of the pending chunk; `next_bytes` = bytes of its successor already resident
+static int launch_pending(fqb_ctx* ctx, uint64_t next_bytes, bool eof)
+{
+    const uint64_t i = ctx->pending_chunk;
+    const uint32_t ds = (uint32_t)(i % ctx->n_dev);
+    fqb_shard sh;
+    memset(&sh, 0, sizeof sh);
+    sh.d_bytes = ctx->d_ring + (size_t)ds * ctx->slot_bytes;
+    sh.n_own = ctx->pending_bytes;
+    sh.n_avail = ctx->pending_bytes + std::min<uint64_t>(next_bytes, MAXREC);
+    sh.stream_offset = ctx->pending_off;
+    sh.flags = ctx->stream_flags | (ctx->pending_line_start ? FQB_F_LINE_START : 0) |
+               ((eof && next_bytes <= MAXREC) ? FQB_F_EOF : 0);
+    if (ctx->stream_flags & FQB_F_INDEX) {
+        DevSlot& d = ctx->dslots[ds];
+        if (!d.d_index) CK(cudaMalloc(&d.d_index, (size_t)ctx->slot_bytes * 4));
+        sh.d_index = d.d_index;
+        sh.index_cap = ctx->slot_bytes;
+    }
+    int rc = enqueue_parse(ctx, &sh, ctx->s_comp, ctx->d_carry, ctx->d_total, false);
+    if (rc) return rc;
+    if (ctx->stream_flags & FQB_F_INDEX) {
+        // generic-closure path: bring this chunk's line ends to the host (needs the count first)
+        CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, ctx->s_comp));
+        CK(cudaStreamSynchronize(ctx->s_comp));
+        uint64_t nl = ctx->h_res->n_lines;
+        uint64_t room = ctx->host_index_cap > ctx->host_index_n ? ctx->host_index_cap - ctx->host_index_n : 0;
+        uint64_t take = std::min(nl, room);
+        if (take && ctx->host_index)
+            CK(cudaMemcpy(ctx->host_index + ctx->host_index_n, sh.d_index, take * 4, cudaMemcpyDeviceToHost));
+        ctx->host_index_n += take;
+    }
+    CK(cudaEventRecord(ctx->dslots[ds].done, ctx->s_comp));
+    ctx->dslots[ds].done_pending = true;
+    ctx->have_pending = false;
+    return FQB_OK;
+}
+
+// copy one chunk (host pointer must stay valid until `copied` fires) into the device ring
+static int submit_chunk(fqb_ctx* ctx, const uint8_t* h_src, uint64_t n, cudaEvent_t copied)
+{
+    const uint64_t i = ctx->chunk_no;
+    const uint32_t ds = (uint32_t)(i % ctx->n_dev);
+    uint8_t* dst = ctx->d_ring + (size_t)ds * ctx->slot_bytes;
+    // the device slot is reused every n_dev chunks: wait for the kernels that read it, and for the
+    // kernel of the chunk before it (it reads this slot's head as its halo)
+    if (ctx->dslots[ds].done_pending) CK(cudaStreamWaitEvent(ctx->s_copy, ctx->dslots[ds].done, 0));
+    const uint32_t prev = (uint32_t)((i + ctx->n_dev - 1) % ctx->n_dev);
+    if (i >= ctx->n_dev && ctx->dslots[prev].done_pending)
+        CK(cudaStreamWaitEvent(ctx->s_copy, ctx->dslots[prev].done, 0));
+    CK(cudaMemcpyAsync(dst, h_src, n, cudaMemcpyHostToDevice, ctx->s_copy));
+    if (ds == 0 && i > 0) {
+        // mirror the head of slot 0 behind the last slot so chunk i-1 sees its successor contiguously
+        uint64_t m = std::min<uint64_t>(n, MAXREC);
+        CK(cudaMemcpyAsync(ctx->d_ring + (size_t)ctx->n_dev * ctx->slot_bytes, dst, m, cudaMemcpyDeviceToDevice,
+                           ctx->s_copy));
+    }
+    CK(cudaEventRecord(copied, ctx->s_copy));
+    CK(cudaStreamWaitEvent(ctx->s_comp, copied, 0));
+    if (ctx->have_pending) {
+        // only the last chunk of a stream is ever shorter than a slot
+        int rc = launch_pending(ctx, n, n < ctx->slot_bytes);
+        if (rc) return rc;
+    }
+    ctx->have_pending = true;
+    ctx->pending_line_start = ctx->last_byte_nl;
+    ctx->last_byte_nl = h_src[n - 1] == '\n';
+    ctx->pending_chunk = i;
+    ctx->pending_bytes = n;
+    ctx->pending_off = ctx->stream_pos;
+    ctx->chunk_no = i + 1;
+    ctx->stream_pos += n;
+    return FQB_OK;
+}
+
+int fqb_stream_acquire(fqb_ctx* ctx, uint8_t** pinned, uint64_t* cap)
+{
+    if (!ctx || !pinned || !cap) return FQB_E_ARG;
+    if (!ctx->streaming || ctx->acquired) return FQB_E_STATE;
+    Slot& s = ctx->slots[ctx->chunk_no % ctx->n_slots];
+    if (ctx->fill == 0 && s.copied_pending) {
+        CK(cudaEventSynchronize(s.copied));  // empty_recv.recv(): wait until the slot has been drained
+        s.copied_pending = false;
+    }
+    *pinned = s.h_pinned + ctx->fill;
+    *cap = ctx->slot_bytes - ctx->fill;
+    ctx->acquired = true;
+    return FQB_OK;
+}
+
+int fqb_stream_submit(fqb_ctx* ctx, uint64_t n_valid)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (!ctx->streaming || !ctx->acquired) return FQB_E_STATE;
+    if (n_valid > ctx->slot_bytes - ctx->fill) return FQB_E_ARG;
+    ctx->acquired = false;
+    ctx->fill += n_valid;
+    if (ctx->fill < ctx->slot_bytes) return FQB_OK;  // short read: the next acquire tops the slot up
+    Slot& s = ctx->slots[ctx->chunk_no % ctx->n_slots];
+    int rc = submit_chunk(ctx, s.h_pinned, ctx->fill, s.copied);
+    s.copied_pending = true;
+    ctx->fill = 0;
+    return rc;
+}
+
+static int stream_drain(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
+{
+    if (ctx->have_pending) {
+        int rc = launch_pending(ctx, 0, true);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(ctx->h_carry, ctx->d_carry, sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_comp));
+    if (host_stats) CK(cudaMemcpyAsync(host_stats, ctx->d_total, ctx->nwords * 8, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    res->status = ctx->h_carry->status;
+    res->finished = ctx->h_carry->status == 0;
+    res->n_records = ctx->h_carry->n_records;
+    res->n_lines = ctx->h_carry->n_lines;
+    res->err_offset = ctx->h_carry->err_offset;
+    res->tail_offset = UINT64_MAX;
+    ctx->streaming = false;
+    return FQB_OK;
+}
+
+int fqb_stream_finish(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
+{
+    if (!ctx || !res) return FQB_E_ARG;
+    if (!ctx->streaming || ctx->acquired) return FQB_E_STATE;
+    if (ctx->fill) {  // partially filled last slot
+        Slot& s = ctx->slots[ctx->chunk_no % ctx->n_slots];
+        int rc = submit_chunk(ctx, s.h_pinned, ctx->fill, s.copied);
+        s.copied_pending = true;
+        ctx->fill = 0;
+        if (rc) {
+            ctx->streaming = false;
+            return rc;
+        }
+    }
+    int rc = stream_drain(ctx, res, host_stats);
+    ctx->streaming = false;
+    return rc;
+}
+
+int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint32_t flags, fqb_result* res,
+                   uint64_t* host_stats, uint32_t* host_index, uint64_t index_cap, uint64_t* n_index)
+{
+    if (!ctx || !res || (n && !bytes)) return FQB_E_ARG;
+    if ((flags & FQB_F_INDEX) && index_cap && !host_index) return FQB_E_ARG;
+    int rc = fqb_stream_begin(ctx, flags);
+    if (rc) return rc;
+    ctx->host_index = host_index;
+    ctx->host_index_cap = host_index ? index_cap : 0;
+    // pinned caller memory is copied from directly; pageable memory goes through the pinned slots
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (n && cudaPointerGetAttributes(&attr, bytes) == cudaSuccess)
+        pinned = attr.type == cudaMemoryTypeHost;
+    else
+        cudaGetLastError();
+    uint64_t off = 0;
+    while (off < n && rc == FQB_OK) {
+        const uint64_t len = std::min<uint64_t>(ctx->slot_bytes, n - off);
+        Slot& s = ctx->slots[ctx->chunk_no % ctx->n_slots];
+        if (s.copied_pending) {
+            cudaError_t e = cudaEventSynchronize(s.copied);
+            if (e != cudaSuccess) {
+                rc = fail(ctx, e, "cudaEventSynchronize");
+                break;
+            }
+            s.copied_pending = false;
+        }
+        const uint8_t* src = bytes + off;
+        if (!pinned) {
+            // stage with a few threads: one memcpy stream cannot keep PCIe busy
+            const int nt = 4;
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; ++k) {
+                uint64_t a = len * k / nt, b = len * (k + 1) / nt;
+                th.emplace_back([=, &s] { memcpy(s.h_pinned + a, src + a, b - a); });
+            }
+            for (auto& t : th) t.join();
+            src = s.h_pinned;
+        }
+        rc = submit_chunk(ctx, src, len, s.copied);
+        s.copied_pending = true;
+        off += len;
+    }
+    if (rc == FQB_OK) rc = stream_drain(ctx, res, host_stats);
+    ctx->streaming = false;
+    if (n_index) *n_index = ctx->host_index_n;
+    ctx->host_index = nullptr;
+    ctx->host_index_cap = 0;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// fq_common.cuh -- shared definitions between the sm_100a kernels and the C-ABI host layer.
+//
+// Path replaced (reference = aseyboldt/fastq-rs 0.6.0):
+//   IdxRecord::from_buffer      src/records.rs:201-247   (4 x memchr('\n') + '@'/'+'/length checks)
+//   RecordRefIter::advance      src/lib.rs:255-303       (refill / carry-over state machine)
+//   Record::seq()/qual()        src/records.rs:82-90     (views the stats closure reads)
+// Design notes live in DESIGN.md.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fq {
+
+constexpr int THREADS = 512;               // 16 warps per CTA
+constexpr int NWARPS = THREADS / 32;
+constexpr int TILE = 16384;                // owned bytes per tile
+constexpr int HALO = 1024;                 // bytes staged after the tile (tails of records that start in it)
+constexpr int FRONT = 16;                  // bytes staged before the tile (only the last one matters)
+constexpr int SM_TILE = FRONT + TILE + HALO;
+constexpr int UNIT = 512;                  // one warp x 16 B
+constexpr int NUNITS = (TILE + HALO) / UNIT;
+constexpr int ITERS = (NUNITS + NWARPS - 1) / NWARPS;
+constexpr int LIST_CAP = 4096;             // newline positions kept in shared memory per tile
+constexpr int HIST_ROWS = 128;             // byte values with a shared-memory counter row (ASCII)
+constexpr int CHUNK_WORDS = HIST_ROWS * 32;  // one 32-position chunk: [byte][lane] u32 (lo16 seq, hi16 qual)
+constexpr uint32_t MAXREC = 68u * 1024u;   // src/lib.rs:129 BUFSIZE
+constexpr unsigned long long NONE64 = ~0ull;
+
+constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0x08, F_FRONT16 = 0x10;
+constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad
+constexpr uint32_t F_CARRY = 0x200;        // internal: streaming, line_base comes from the carry block
+
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
+
+// device-resident outcome of one parse (mirrors fqb_result, plus scratch)
+struct DevResult {
+    unsigned long long first_bad;   // buffer-relative offset of the first bad record (atomicMin)
+    unsigned long long tail_start;  // buffer-relative offset of the first incomplete-not-bad record
+    unsigned long long n_lines;     // '\n' in [0, n_own)
+    unsigned long long line_end;    // line_base + n_lines
+    unsigned long long err_offset;  // stream offset
+    unsigned long long n_records;
+    int status;
+    int finished;
+};
+
+// streaming carry block (device resident, lives across chunk launches)
+struct DevCarry {
+    unsigned long long line_base;   // lines before the next chunk
+    unsigned long long n_records;   // records delivered so far
+    unsigned long long err_offset;
+    unsigned long long n_lines;
+    int status;                     // sticky first error
+    int pad;
+};
+
+struct ScanParams {
+    const uint8_t* data;
+    unsigned long long n_own, n_avail;
+    unsigned long long stream_offset;
+    unsigned long long line_base;
+    const DevCarry* carry;          // F_CARRY
+    uint32_t flags;
+    uint32_t max_len;               // P
+    uint32_t ntiles;
+    uint32_t pad;
+    unsigned long long* tile_status;
+    unsigned int* ticket;
+    uint32_t* index;
+    unsigned long long index_cap;
+    DevResult* res;
+    unsigned long long* stats;      // stats block
+    unsigned long long* seqraw;     // [P][256] raw byte histogram of the sequence lines
+};
+
+__host__ __device__ inline size_t stats_len_off(uint32_t) { return 8; }
+__host__ __device__ inline size_t stats_base_off(uint32_t P) { return 8 + (size_t)P + 2; }
+__host__ __device__ inline size_t stats_qual_off(uint32_t P) { return 8 + (size_t)P + 2 + 6 * (size_t)P; }
+__host__ __device__ inline size_t stats_words(uint32_t P) { return 8 + (size_t)P + 2 + 6 * (size_t)P + 256 * (size_t)P; }
+
+// launchers (fq_kernels.cu)
+size_t scan_smem_bytes(int nchunk);
+cudaError_t scan_configure();
+int scan_blocks_per_sm(int nchunk);
+cudaError_t launch_scan(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
+cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t st);
+cudaError_t launch_rerun_reset(const ScanParams& p, cudaStream_t st);
+cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
+cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);
+cudaError_t launch_synth_fixed(uint8_t* out, unsigned long long n, unsigned long long byte_off, uint32_t L,
+                               unsigned long long seed, cudaStream_t st);
+cudaError_t launch_synth_var(uint8_t* out, const unsigned long long* rec_off, unsigned long long first,
+                             unsigned long long count, unsigned long long seed, cudaStream_t st);
+cudaError_t launch_synth_var_sizes(unsigned long long* sizes, unsigned long long first, unsigned long long count,
+                                   unsigned long long seed, cudaStream_t st);
+
+}  // namespace fq

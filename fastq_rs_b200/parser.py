@@ -1,0 +1,317 @@
+"""Host-side mirror of the `fastq` crate's interface for the delimiting path.
+
+Same names, argument meaning and error behaviour as the reference (aseyboldt/fastq-rs 0.6.0):
+
+    Parser(reader).each(func) -> bool                      src/lib.rs:221-238
+    Parser(reader).parallel_each(n_threads, func) -> list  src/lib.rs:509-566
+    Parser(reader).ref_iter() -> RecordRefIter             src/lib.rs:208, 241-304
+    RecordSet.iter()/len()/is_empty()                      src/lib.rs:306-336
+    Record: head()/seq()/qual()/write()/validate_dna(n)()  src/records.rs:5-34
+    RefRecord / OwnedRecord / to_owned_record              src/records.rs:36-54,93-129,165-175
+    each_zipped(parser1, parser2, callback)                src/lib.rs:577-609
+
+plus the fast paths that never materialise records on the host: Parser.count(), Parser.stats().
+
+Record delimiting ('\n' scan, '@'/'+'/length validation, record offsets) always runs on the GPU
+through the C ABI; closures run here over the returned index, borrowing the caller's bytes.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Callable, Iterator, Optional
+
+import numpy as np
+
+from .engine import Engine, FastqError, Outcome, Stats
+
+BUFSIZE = 68 * 1024  # src/lib.rs:129
+
+_default_engines: dict = {}
+
+
+def default_engine(max_len: int = 150, device: int = 0) -> Engine:
+    key = (max_len, device)
+    if key not in _default_engines:
+        _default_engines[key] = Engine(max_len=max_len, device=device, slot_bytes=8 << 20)
+    return _default_engines[key]
+
+
+def _trim_winline(b: bytes) -> bytes:  # src/records.rs:65-73
+    return b[:-1] if b.endswith(b"\r") else b
+
+
+class OwnedRecord:  # src/records.rs:49-54, 99-129
+    def __init__(self, head: bytes, seq: bytes, sep: Optional[bytes], qual: bytes):
+        self._head, self._seq, self.sep, self._qual = head, seq, sep, qual
+
+    def head(self) -> bytes:
+        return self._head
+
+    def seq(self) -> bytes:
+        return self._seq
+
+    def qual(self) -> bytes:
+        return self._qual
+
+    def write(self, writer) -> int:
+        parts = [b"@", self._head, b"\n", self._seq, b"\n", self.sep if self.sep is not None else b"+",
+                 b"\n", self._qual, b"\n"]
+        n = 0
+        for p in parts:
+            writer.write(p)
+            n += len(p)
+        return n
+
+    def validate_dna(self) -> bool:
+        return all(c in b"ACTG" for c in self._seq)
+
+    def validate_dnan(self) -> bool:
+        return all(c in b"ACTGN" for c in self._seq)
+
+    def __eq__(self, o):
+        return isinstance(o, OwnedRecord) and (self._head, self._seq, self.sep, self._qual) == \
+            (o._head, o._seq, o.sep, o._qual)
+
+
+class RefRecord:
+    """Borrowed view (src/records.rs:36-45): `data` is the record's bytes, head/seq/sep/qual the
+    record-relative offsets of its four line ends."""
+    __slots__ = ("data", "_head", "_seq", "_sep", "_qual", "offset")
+
+    def __init__(self, data: memoryview, head: int, seq: int, sep: int, qual: int, offset: int):
+        self.data, self._head, self._seq, self._sep, self._qual, self.offset = data, head, seq, sep, qual, offset
+
+    def head(self) -> bytes:  # skips '@'
+        return _trim_winline(bytes(self.data[1:self._head]))
+
+    def seq(self) -> bytes:
+        return _trim_winline(bytes(self.data[self._head + 1:self._seq]))
+
+    def qual(self) -> bytes:
+        return _trim_winline(bytes(self.data[self._sep + 1:self._qual]))
+
+    def write(self, writer) -> int:
+        writer.write(bytes(self.data))
+        return len(self.data)
+
+    def validate_dna(self) -> bool:
+        return all(c in b"ACTG" for c in self.seq())
+
+    def validate_dnan(self) -> bool:
+        return all(c in b"ACTGN" for c in self.seq())
+
+    def to_owned_record(self) -> OwnedRecord:  # src/records.rs:165-175
+        return OwnedRecord(self.head(), self.seq(),
+                           _trim_winline(bytes(self.data[self._seq + 1:self._sep])), self.qual())
+
+
+class RecordSet:  # src/lib.rs:306-336
+    def __init__(self, buf: memoryview, starts: np.ndarray, ends4: np.ndarray):
+        self._buf, self._starts, self._ends = buf, starts, ends4
+
+    def iter(self) -> Iterator[RefRecord]:
+        for i in range(len(self._starts)):
+            yield _make_record(self._buf, int(self._starts[i]), self._ends[i])
+
+    __iter__ = iter
+
+    def len(self) -> int:
+        return len(self._starts)
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return len(self._starts) == 0
+
+
+def _make_record(buf: memoryview, start: int, ends) -> RefRecord:
+    e0, e1, e2, e3 = (int(x) for x in ends)
+    return RefRecord(buf[start:e3 + 1], e0 - start, e1 - start, e2 - start, e3 - start, start)
+
+
+def _read_all(reader) -> np.ndarray:
+    if isinstance(reader, np.ndarray):
+        return np.ascontiguousarray(reader.view(np.uint8))
+    if isinstance(reader, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(reader), dtype=np.uint8)
+    chunks = []
+    while True:
+        b = reader.read(1 << 22)
+        if not b:
+            break
+        chunks.append(b)
+    return np.frombuffer(b"".join(chunks), dtype=np.uint8)
+
+
+class _Delimited:
+    """Result of the GPU delimiting pass over one stream: record starts and line ends."""
+
+    def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray):
+        n = outcome.n_records
+        ends = index[:4 * n].astype(np.int64).reshape(n, 4)
+        starts = np.empty(n, dtype=np.int64)
+        if n:
+            starts[0] = 0
+            starts[1:] = ends[:-1, 3] + 1
+        self.buf = memoryview(data)
+        self.outcome, self.starts, self.ends = outcome, starts, ends
+
+
+class RecordRefIter:  # src/lib.rs:241-304
+    def __init__(self, d: _Delimited):
+        self._d, self._i, self._cur = d, -1, None
+
+    def advance(self) -> None:
+        self._i += 1
+        if self._i < len(self._d.starts):
+            self._cur = _make_record(self._d.buf, int(self._d.starts[self._i]), self._d.ends[self._i])
+        else:
+            self._cur = None
+            self._d.outcome.raise_for_status()  # Err only after every earlier record was handed out
+
+    def get(self) -> Optional[RefRecord]:
+        return self._cur
+
+
+class Parser:
+    """Parser::new(reader) (src/lib.rs:200).  `reader`: bytes-like, uint8 ndarray, or an object
+    with .read().  `max_len` = positions tracked by stats()."""
+
+    def __init__(self, reader, engine: Optional[Engine] = None, max_len: int = 150):
+        self._reader = reader
+        self._engine = engine or default_engine(max_len)
+
+    def _delimit(self) -> _Delimited:
+        data = _read_all(self._reader)
+        outcome, _, index = self._engine.parse_host(data, hist=False, want_index=True, want_stats=False)
+        return _Delimited(data, outcome, index)
+
+    def ref_iter(self) -> RecordRefIter:
+        return RecordRefIter(self._delimit())
+
+    def each(self, func: Callable[[RefRecord], bool]) -> bool:
+        """Apply func to every record; stop if it returns False.  Returns True at end of input,
+        False if the closure stopped; raises FastqError -- after all earlier records were
+        delivered -- on bad input."""
+        it = self.ref_iter()
+        while True:
+            it.advance()
+            rec = it.get()
+            if rec is None:
+                return True
+            if not func(rec):
+                return False
+
+    def record_sets(self) -> Iterator[RecordSet]:
+        """Batches of records whose bytes span at most BUFSIZE (src/lib.rs:364-425).  As in the
+        reference, an error surfaces when the batch holding the bad record would be produced,
+        and that batch is dropped."""
+        d = self._delimit()
+        n = len(d.starts)
+        i = 0
+        while i < n:
+            j = int(np.searchsorted(d.ends[:, 3], d.starts[i] + BUFSIZE - 1, side="right"))
+            j = max(j, i + 1)
+            if j >= n and d.outcome.status != 0:
+                break  # the batch that would end at the bad record is dropped (src/lib.rs:375,399-410)
+            yield RecordSet(d.buf, d.starts[i:j], d.ends[i:j])
+            i = j
+        d.outcome.raise_for_status()
+
+    def parallel_each(self, n_threads: int, func: Callable[[Iterator[RecordSet]], object]) -> list:
+        """n_threads workers, each fed RecordSets round-robin over a bounded queue of 10
+        (src/lib.rs:509-566).  Returns the workers' results in worker order; raises FastqError on
+        bad input (after joining the workers)."""
+        queues = [queue.Queue(maxsize=10) for _ in range(n_threads)]
+        results: list = [None] * n_threads
+        errors: list = [None] * n_threads
+        DONE = object()
+
+        def worker(i):
+            def sets():
+                while True:
+                    s = queues[i].get()
+                    if s is DONE:
+                        return
+                    yield s
+            try:
+                results[i] = func(sets())
+            except BaseException as e:  # worker panic -> re-raised on join (src/lib.rs:558)
+                errors[i] = e
+            finally:
+                while True:  # drain so the producer never blocks on a dead worker
+                    try:
+                        if queues[i].get_nowait() is DONE:
+                            break
+                    except queue.Empty:
+                        break
+
+        threads = [threading.Thread(target=worker, args=(i,), name=f"worker-{i}") for i in range(n_threads)]
+        for t in threads:
+            t.start()
+        err = None
+        try:
+            if n_threads:
+                for k, s in enumerate(self.record_sets()):
+                    queues[k % n_threads].put(s)
+        except FastqError as e:
+            err = e
+        for q in queues:
+            q.put(DONE)
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        if err is not None:
+            raise err
+        return results
+
+    # ---- fast paths: nothing but counts / histograms ever reaches the host -------------------
+    def count(self) -> int:
+        """examples/fastq-count.rs: number of records (raises on bad input)."""
+        data = _read_all(self._reader)
+        outcome, _, _ = self._engine.parse_host(data, hist=False, want_stats=False)
+        outcome.raise_for_status()
+        return outcome.n_records
+
+    def stats(self) -> tuple[Outcome, Stats]:
+        """The stats closure (per-position base / quality histograms over seq()/qual()) run on the
+        GPU; Outcome.status tells whether (and where) each() would have returned Err."""
+        data = _read_all(self._reader)
+        outcome, st, _ = self._engine.parse_host(data, hist=True)
+        return outcome, st
+
+
+def each_zipped(parser1: Parser, parser2: Parser, callback) -> tuple[bool, bool]:
+    """src/lib.rs:577-609, lock-step over two delimited streams."""
+    it1, it2 = parser1.ref_iter(), parser2.ref_iter()
+    finished = (False, False)
+    it1.advance()
+    it2.advance()
+    while True:
+        v1 = None if finished[0] else it1.get()
+        v2 = None if finished[1] else it2.get()
+        finished = (v1 is None, v2 is None)
+        adv = callback(v1, v2)
+        if tuple(adv) == (False, False) or finished == (True, True):
+            return finished
+        if adv[0] and not finished[0]:
+            it1.advance()
+        if adv[1] and not finished[1]:
+            it2.advance()
+
+
+def parse_path(path, func, max_len: int = 150):
+    """src/lib.rs:167-196 for uncompressed input: open `path` (None / '-' = stdin) and hand a
+    Parser to func.  Decompression (niffler) is outside the accelerated path."""
+    import sys
+    if path is None or path == "-":
+        return func(Parser(sys.stdin.buffer, max_len=max_len))
+    with open(path, "rb") as f:
+        magic = f.read(4)
+        f.seek(0)
+        if magic[:2] == b"\x1f\x8b" or magic[:3] == b"BZh" or magic[:4] in (b"\xfd7zX", b"\x04\"M\x18"):
+            raise FastqError(6, 0, 0)
+        return func(Parser(f, max_len=max_len))

@@ -1,0 +1,181 @@
+/*
+ * fastq_b200.h -- C ABI of the B200-native FASTQ delimit + per-record statistics engine.
+ *
+ * This is the drop-in boundary for ONE path of the `fastq` crate (aseyboldt/fastq-rs 0.6.0):
+ * record delimiting with '@'/'+' validation over raw bytes, plus the per-position base and
+ * quality histograms a stats closure would compute over Record::seq()/qual().  Everything
+ * here is `extern "C"`, plain pointers and sizes -- what a Rust `extern "C"` block (or cgo /
+ * ctypes) binds.  No callbacks cross this boundary: closures run on the caller's side over
+ * the record index this library returns (see INTEGRATION.md and rust/).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the crate).
+ * The CUDA extension is the only implementation: there is no CPU fallback behind this ABI.
+ */
+#ifndef FASTQ_B200_H
+#define FASTQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQB_ABI_VERSION 1u
+
+/* ---- status codes --------------------------------------------------------------------
+ * 1..5 are the reference's grammar errors; the host shim maps each to
+ * io::Error::new(InvalidData, <message>) with the exact reference text. */
+enum {
+    FQB_OK = 0,
+    FQB_E_HEADER = 1,    /* "Fastq headers must start with '@'"        src/records.rs:143-146 */
+    FQB_E_SEP = 2,       /* "Sequence and quality not separated by +"  src/records.rs:157-160 */
+    FQB_E_LENGTH = 3,    /* "Sequence and quality length mismatch"     src/records.rs:233-238 */
+    FQB_E_TOO_LONG = 4,  /* "Fastq record is too long"                 src/lib.rs:278-283     */
+    FQB_E_TRUNCATED = 5, /* "Possibly truncated input file"            src/lib.rs:286-291     */
+    FQB_E_IO = 6,        /* reader error passed through                src/buffer.rs:86-96    */
+    FQB_E_ARG = 50,      /* bad argument (null pointer, misaligned buffer, ...) */
+    FQB_E_STATE = 51,    /* call out of order (e.g. submit without acquire) */
+    FQB_E_NOMEM = 52,
+    FQB_E_CUDA = 100     /* CUDA runtime failure; fqb_last_error() has the text */
+};
+
+/* The reference refuses records that do not fit its 68 KiB window (src/lib.rs:129,278-283).
+ * Here: a record (start '@' .. final '\n' inclusive) longer than this is FQB_E_TOO_LONG. */
+#define FQB_MAX_RECORD_BYTES (68u * 1024u)
+
+/* ---- flags for fqb_shard.flags -------------------------------------------------------- */
+#define FQB_F_HIST        0x01u /* accumulate the per-position histograms (stats closure)   */
+#define FQB_F_INDEX       0x02u /* write the line-end index (record offsets)                */
+#define FQB_F_LINE_START  0x04u /* byte 0 of the buffer is the first byte of a line (stream
+                                   start, or the byte before it is '\n')                   */
+#define FQB_F_EOF         0x08u /* no byte of the stream exists beyond n_avail              */
+#define FQB_F_FRONT16     0x10u /* d_bytes[-16..0) is readable and holds the 16 stream bytes
+                                   before the shard (lets the kernel see whether the shard
+                                   starts right after a '\n'); excludes FQB_F_LINE_START    */
+
+typedef struct fqb_ctx fqb_ctx;
+
+typedef struct {
+    uint32_t abi_version;   /* FQB_ABI_VERSION */
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t max_len;       /* P: positions tracked per read (150, 300, ...), 1..4096 */
+    uint32_t reserved0;
+    uint64_t slot_bytes;    /* streaming: bytes per pinned/device ring slot (0 = 64 MiB) */
+    uint32_t n_slots;       /* streaming: ring depth (0 = 3); mirrors thread_reader's queuelen
+                               (src/thread_reader.rs:13-32) */
+    uint32_t reserved1;
+} fqb_config;
+
+/* One contiguous piece of a byte stream resident in device memory.
+ * Records are OWNED by the shard in which their first byte lies ([0, n_own)); their tails
+ * may extend into [n_own, n_avail) -- the device-side counterpart of the carry-over that
+ * Buffer::clean / replace_buffer perform (src/buffer.rs:30-72). */
+typedef struct {
+    const uint8_t *d_bytes; /* device pointer, 16-byte aligned */
+    uint64_t n_own;
+    uint64_t n_avail;       /* >= n_own; bytes readable */
+    uint64_t stream_offset; /* stream offset of d_bytes[0] (reported in err_offset, index) */
+    uint64_t line_base;     /* number of '\n' in the stream before d_bytes[0]: fixes which
+                               lines are headers (strict 4-line cadence, src/records.rs:201-247) */
+    uint32_t flags;         /* FQB_F_* */
+    uint32_t reserved;
+    uint32_t *d_index;      /* FQB_F_INDEX: device array receiving, for the i-th '\n' of
+                               [0, n_own), the low 32 bits of its stream offset (the four line
+                               ends of IdxRecord, src/records.rs:56-63, laid out densely:
+                               record k of the shard = entries 4k'..4k'+3 after the phase) */
+    uint64_t index_cap;     /* entries available in d_index */
+} fqb_shard;
+
+/* Outcome of a parse: what Parser::each returns (src/lib.rs:221-238) plus where it stopped. */
+typedef struct {
+    int32_t status;        /* FQB_OK or FQB_E_* of the FIRST bad record in stream order */
+    int32_t finished;      /* 1 = reached the end of the shard/stream cleanly */
+    uint64_t n_records;    /* records delivered = all records before the first bad one */
+    uint64_t n_lines;      /* '\n' bytes in the owned range */
+    uint64_t err_offset;   /* stream offset of the record at which the error was raised */
+    uint64_t tail_offset;  /* stream offset of the first owned record that is incomplete within
+                              n_avail without being an error (only without FQB_F_EOF);
+                              UINT64_MAX if none */
+} fqb_result;
+
+/* Statistics block: a flat array of uint64_t, fqb_stats_words(P) long, laid out
+ *   [0] n_records  [1] n_bases  [2] clip_seq  [3] clip_qual  [4..7] reserved
+ *   [8 .. 8+P+2)                len_hist[min(len, P+1)]
+ *   [.. + 6P)                   base_hist[pos][A,C,G,T,N,other]
+ *   [.. + 256P)                 qual_hist[pos][raw byte]
+ * computed over Record::seq()/qual() (src/records.rs:82-90: one trailing '\r' trimmed),
+ * base classes as validate_dnan's alphabet (src/records.rs:29-33).  One block = one
+ * ncclAllReduce(sum, u64) payload. */
+#define FQB_STATS_HDR 8u
+size_t fqb_stats_words(uint32_t max_len);
+size_t fqb_stats_len_hist_off(uint32_t max_len);
+size_t fqb_stats_base_hist_off(uint32_t max_len);
+size_t fqb_stats_qual_hist_off(uint32_t max_len);
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* replaces Parser::new (src/lib.rs:200-205): owns all device/pinned resources */
+int fqb_create(const fqb_config *cfg, fqb_ctx **out);
+void fqb_destroy(fqb_ctx *ctx);
+const char *fqb_strerror(int status);     /* reference message for 1..5 */
+const char *fqb_last_error(fqb_ctx *ctx); /* detail for FQB_E_CUDA etc. */
+uint32_t fqb_abi_version(void);
+
+/* ---- in-HBM path (bytes already resident on the device) --------------------------------
+ * replaces Parser::each + the stats closure over one shard (src/lib.rs:221-238,
+ * src/records.rs:201-247).  Asynchronous on `stream` (a cudaStream_t, NULL = default). */
+int fqb_parse_device(fqb_ctx *ctx, const fqb_shard *shard, void *stream);
+/* count '\n' in d_bytes[0..n) (the line-phase exchange between shards; also what
+ * `wc -l` measures, README.md:41).  Asynchronous; result via fqb_fetch_line_count. */
+int fqb_count_lines_device(fqb_ctx *ctx, const uint8_t *d_bytes, uint64_t n, void *stream);
+int fqb_fetch_line_count(fqb_ctx *ctx, void *stream, uint64_t *n_lines);
+/* wait for `stream`, copy out the outcome and (if host_stats != NULL) the stats block */
+int fqb_fetch(fqb_ctx *ctx, void *stream, fqb_result *res, uint64_t *host_stats);
+/* device address of the stats block of the last parse (for an in-place allreduce) */
+uint64_t *fqb_device_stats(fqb_ctx *ctx);
+/* number of kernels this library launched on ctx so far (bench accounting) */
+uint64_t fqb_launch_count(fqb_ctx *ctx);
+/* CUDA-event time of the main scan kernel of the last fqb_parse_device call, in ms
+ * (waits for it); <0 on error */
+float fqb_last_scan_ms(fqb_ctx *ctx);
+
+/* ---- host path: bytes in host memory, staged through the pinned ring --------------------
+ * replaces Parser::new(reader).each(stats closure) end to end.  Synchronous.
+ * host_index (optional): receives the low 32 bits of the stream offset of every '\n'
+ * before the first bad record, up to index_cap entries; *n_index = entries written. */
+int fqb_parse_host(fqb_ctx *ctx, const uint8_t *bytes, uint64_t n, uint32_t flags,
+                   fqb_result *res, uint64_t *host_stats,
+                   uint32_t *host_index, uint64_t index_cap, uint64_t *n_index);
+
+/* ---- streaming ring: the thread_reader protocol on pinned slots --------------------------
+ * (src/thread_reader.rs:13-50: `empty` -> reader fills -> `full` -> consumer -> `empty`)   */
+int fqb_stream_begin(fqb_ctx *ctx, uint32_t flags);
+/* blocks until a pinned slot is free (empty_recv.recv(), src/thread_reader.rs:44) */
+int fqb_stream_acquire(fqb_ctx *ctx, uint8_t **pinned, uint64_t *cap);
+/* hand the filled slot over (full_send.send(), src/thread_reader.rs:46): enqueues the
+ * H2D copy on the copy stream and the kernels on the compute stream */
+int fqb_stream_submit(fqb_ctx *ctx, uint64_t n_valid);
+/* end of input: drains the ring, returns outcome + stats */
+int fqb_stream_finish(fqb_ctx *ctx, fqb_result *res, uint64_t *host_stats);
+
+/* ---- pinned host memory helpers ------------------------------------------------------- */
+int fqb_host_alloc(uint64_t bytes, void **out); /* cudaHostAlloc */
+void fqb_host_free(void *p);
+
+/* ---- synthetic FASTQ; device twin of the oracle generator -------------- */
+#define FQB_SYNTH_SEED 0xFA57A11CE5EED001ull
+/* bytes [byte_off, byte_off+n) of the infinite fixed-length stream (read length L) */
+int fqb_synth_fixed_device(uint8_t *d_out, uint64_t n, uint64_t byte_off, uint32_t L,
+                           uint64_t seed, void *stream);
+/* variable-length records [first, first+count); d_rec_off[i] = byte offset of record
+ * first+i relative to d_out (count+1 entries, exclusive prefix sum of record sizes) */
+int fqb_synth_var_device(uint8_t *d_out, const uint64_t *d_rec_off, uint64_t first,
+                         uint64_t count, uint64_t seed, void *stream);
+/* record sizes (bytes) of variable-length records [first, first+count) into d_sizes */
+int fqb_synth_var_sizes_device(uint64_t *d_sizes, uint64_t first, uint64_t count,
+                               uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTQ_B200_H */

@@ -1,0 +1,509 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle.
+
+Bar: bit-exact for record counts, record offsets, error kind + offset, and every histogram bin.
+Covers the reference's own unit tests (tests/golden/reference_unit_tests.json, src/lib.rs:611-811),
+the edge-case list of SURVEY.md 8(a), synthetic inputs A/B of 8(d), shard cuts at every byte,
+the streaming ring with chunk boundaries, and hypothesis-mutated inputs.
+"""
+import base64
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_unit_tests.json")) as f:
+    GOLD = json.load(f)
+
+
+def d64(s):
+    return base64.b64decode(s)
+
+
+def vec_input(v) -> bytes:
+    if "input" in v:
+        return d64(v["input"])
+    g = v["input_gen"]
+    return d64(g["prefix"]) + d64(g["unit"]) * g["times"] + d64(g["suffix"])
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import fastq_rs_b200 as fq
+    return fq
+
+
+@pytest.fixture(scope="module")
+def eng(fq):
+    e = fq.Engine(max_len=150, slot_bytes=1 << 20)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng300(fq):
+    e = fq.Engine(max_len=300, slot_bytes=1 << 20)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng16(fq):
+    e = fq.Engine(max_len=16, slot_bytes=1 << 20)
+    yield e
+    e.close()
+
+
+def to_dev(torch, data: bytes, pad: int = 64):
+    a = np.frombuffer(data, dtype=np.uint8)
+    t = torch.zeros(len(data) + pad, dtype=torch.uint8, device="cuda")
+    if len(data):
+        t[:len(data)] = torch.from_numpy(a.copy())
+    return t
+
+
+def assert_stats_equal(st, ost):
+    assert st.n_records == ost.n_records
+    assert st.n_bases == ost.n_bases
+    assert st.clip_seq == ost.clip_seq
+    assert st.clip_qual == ost.clip_qual
+    np.testing.assert_array_equal(st.len_hist, ost.len_hist)
+    np.testing.assert_array_equal(st.base_hist, ost.base_hist)
+    np.testing.assert_array_equal(st.qual_hist, ost.qual_hist)
+
+
+def check_device_vs_oracle(torch, oracle, engine, data: bytes, check_index=True):
+    """parse_device over the whole buffer == oracle.each on the same bytes."""
+    P = engine.max_len
+    t = to_dev(torch, data)
+    idx = torch.zeros(len(data) + 8, dtype=torch.int32, device="cuda")
+    engine.parse_device(t, n_own=len(data), n_avail=len(data), hist=True, index=idx)
+    out, st = engine.fetch()
+    ores, ost = oracle.each_stats(data, P)
+    assert out.status == ores.status, (out, ores)
+    assert out.n_records == ores.n_records
+    if ores.status != 0:
+        assert out.err_offset == ores.err_offset
+        assert not out.finished
+    else:
+        assert out.finished
+    assert out.n_lines == data.count(b"\n")
+    assert_stats_equal(st, ost)
+    if check_index:
+        _, oidx = oracle.each_index(data)
+        n = out.n_records
+        got = idx[:4 * n].cpu().numpy().view(np.uint32).astype(np.uint64).reshape(n, 4)
+        np.testing.assert_array_equal(got, oidx[:, 1:5])
+        if n:
+            starts = np.concatenate([[0], got[:-1, 3] + 1]).astype(np.uint64)
+            np.testing.assert_array_equal(starts, oidx[:, 0])
+    # the host path (pinned ring, chunked) must agree too
+    hout, hst, hidx = engine.parse_host(data, want_index=True)
+    assert (hout.status, hout.n_records) == (ores.status, ores.n_records)
+    if ores.status != 0:
+        assert hout.err_offset == ores.err_offset
+    assert_stats_equal(hst, ost)
+    return out, st
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's own unit tests
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("v", GOLD["vectors"], ids=[v["name"] for v in GOLD["vectors"]])
+def test_reference_unit_test(v, fq, torch, oracle, eng):
+    data = vec_input(v)
+    exp = v["expect"]
+    recs = []
+    err = None
+    try:
+        if v["api"] == "each":
+            finished = fq.Parser(data, engine=eng).each(lambda r: recs.append(r.to_owned_record()) or True)
+            assert finished
+        elif v["api"] == "record_sets":
+            for s in fq.Parser(data, engine=eng).record_sets():
+                recs.extend(r.to_owned_record() for r in s)
+        elif v["api"] == "parallel_each":
+            counts = fq.Parser(data, engine=eng).parallel_each(
+                v["n_threads"], lambda sets: sum(s.len() for s in sets))
+            assert sum(counts) == exp["count"]
+    except fq.FastqError as e:
+        err = e
+    assert (err is None) == exp["ok"]
+    if err is not None:
+        assert err.kind == "InvalidData"
+        if "expect_kind" in v:
+            assert oracle.ERR_NAMES[err.status] == v["expect_kind"]
+    if "records" in exp and v["api"] != "parallel_each":
+        assert len(recs) == len(exp["records"])
+        for r, e in zip(recs, exp["records"]):
+            assert r.head() == d64(e["head"]) and r.seq() == d64(e["seq"]) and r.qual() == d64(e["qual"])
+            if "write" in e:
+                w = io.BytesIO()
+                assert r.write(w) == len(d64(e["write"]))
+                assert w.getvalue() == d64(e["write"])
+    if "count" in exp and v["api"] == "record_sets" and exp["ok"]:
+        assert len(recs) == exp["count"]
+    check_device_vs_oracle(torch, oracle, eng, data)
+
+
+def test_refrecord_write_verbatim(fq, eng):
+    data = b"@hi\r\nNN\r\n+hi\r\n++\r\n"
+    out = []
+    fq.Parser(data, engine=eng).each(lambda r: out.append((r.head(), r.seq(), r.qual(), bytes(r.data))) or True)
+    assert out == [(b"hi", b"NN", b"++", data)]
+
+
+def test_each_stops_when_closure_returns_false(fq, eng, oracle):
+    data = oracle.synth_fixed_records(10).tobytes()
+    seen = []
+    assert fq.Parser(data, engine=eng).each(lambda r: seen.append(1) or len(seen) < 3) is False
+    assert len(seen) == 3
+
+
+# --------------------------------------------------------------------------------------------
+# edge cases
+# --------------------------------------------------------------------------------------------
+EDGE = {
+    "empty": b"",
+    "lone_newline": b"\n",
+    "trailing_blank_line": b"@a\nAC\n+\n!!\n\n",
+    "empty_seq": b"@id\n\n+\n\n",
+    "empty_seq_many": b"@\n\n+\n\n" * 50,
+    "crlf": b"@hi\r\nNN\r\n+\r\n++\r\n@ho\r\nACGT\r\n+\r\n!!!!\r\n",
+    "mixed_mismatch": b"@hi\nNN\r\n+\n++\n",
+    "mixed_accepted": b"@hi\nNN\r\n+\n+++\n",
+    "lone_cr_lines": b"@hi\n\r\n+\n\r\n",
+    "qual_starts_with_at": b"@id\nAC\n+\n@+\n@id2\nGT\n+\n+@\n",
+    "partial_sep_error": b"@a\nAC\n+\n!!\n@hi\nNN\nX",
+    "partial_header_error": b"@a\nAC\n+\n!!\nhi",
+    "partial_truncated": b"@a\nAC\n+\n!!\n@hi\nNN\n",
+    "partial_truncated2": b"@a\nAC\n+\n!!\n@hi\nNN\n+",
+    "no_final_newline": b"@hi\nNN\n+\n++",
+    "header_error_first": b"hi\nNN\n+\n++\n",
+    "sep_error": b"@hi\nNN\n-\n++\n",
+    "sep_empty_line": b"@hi\nNN\n\n++\n",
+    "length_error_second": b"@a\nAC\n+\n!!\n@b\nACG\n+\n!!\n@c\nA\n+\n!\n",
+    "lowercase_and_other": b"@a\nacgtnXYZ.*\n+\n!!!!!!!!!!\n",
+    "nonascii": b"@a\nAC\xc3\xa9GT\n+\n\x80\xff!!~\x7f\n@b\nAC\n+\n\xfe\x01\n",
+    "tabs_nul": b"@a\tb\x00\nA\x00C\n+\n\x00\t!\n",
+    "only_newlines": b"\n" * 100,
+    "many_blank_after": b"@a\nAC\n+\n!!\n" + b"\n" * 9000,
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+def test_edge_case(name, torch, oracle, eng):
+    check_device_vs_oracle(torch, oracle, eng, EDGE[name])
+
+
+def test_edge_case_small_P(torch, oracle, eng16):
+    # reads longer than P: clip counters and the len_hist overflow bin
+    data = b"@a\n" + b"ACGTN" * 8 + b"\n+\n" + b"I" * 40 + b"\n@b\nACG\n+\n!!!\n"
+    out, st = check_device_vs_oracle(torch, oracle, eng16, data)
+    assert st.clip_seq == 24 and st.clip_qual == 24
+
+
+def _rec(i, L, crlf=False):
+    rng = np.random.default_rng(i)
+    seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), L))
+    qual = bytes(rng.integers(33, 75, L, dtype=np.uint8))
+    e = b"\r\n" if crlf else b"\n"
+    return b"@r%d" % i + e + seq + e + b"+" + e + qual + e
+
+
+def test_long_records_beyond_halo(torch, oracle, eng, eng300):
+    # records longer than the 1 KiB halo take the global-memory path; positions >= P are clipped
+    data = b"".join(_rec(i, L) for i, L in enumerate([10, 1500, 150, 5000, 33000, 2, 20000, 150, 150]))
+    check_device_vs_oracle(torch, oracle, eng, data)
+    check_device_vs_oracle(torch, oracle, eng300, data)
+
+
+def test_record_at_size_limit(torch, oracle, eng):
+    # exactly BUFSIZE bytes at stream start is accepted (test `bufflen`, src/lib.rs:752-774)
+    ok = b"@" + b"a" * (68 * 1024 - 8) + b"\nA\n+\nB\n"
+    assert len(ok) == 68 * 1024
+    check_device_vs_oracle(torch, oracle, eng, ok + _rec(1, 20))
+    # clearly too long
+    bad = _rec(0, 30) + b"@" + b"longid" * (68 * 1024) + b"\nA\n+\nB\n"
+    out, _ = check_device_vs_oracle(torch, oracle, eng, bad)
+    assert out.status == 4 and out.n_records == 1
+    # long sequence line that never ends
+    bad2 = _rec(0, 30) + b"@x\n" + b"A" * 100000
+    out, _ = check_device_vs_oracle(torch, oracle, eng, bad2)
+    assert out.status == 4
+
+
+def test_dense_newlines_list_overflow(torch, oracle, eng):
+    # > LIST_CAP newlines in one 16 KiB tile: 6-byte records (empty seq/qual) and 8-byte records
+    data = b"@\n\n+\n\n" * 6000 + b"@a\nA\n+\n!\n" * 3000 + b"@\n\n+\n\n" * 100
+    check_device_vs_oracle(torch, oracle, eng, data)
+    bad = b"@\n\n+\n\n" * 5000 + b"X\n\n+\n\n" + b"@\n\n+\n\n" * 100
+    out, _ = check_device_vs_oracle(torch, oracle, eng, bad)
+    assert out.status == 1 and out.n_records == 5000
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs A (fixed 150 bp) and B (variable 50..300 bp), device generator == oracle generator
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_rec,off", [(1, 0), (7, 0), (1000, 0), (31152, 0), (500, 321 * 12345678901 + 17)])
+def test_synth_fixed_generator_and_parse(n_rec, off, torch, oracle, eng):
+    n = n_rec * 321
+    t = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    eng.synth_fixed(t, n, byte_off=off)
+    torch.cuda.synchronize()
+    got = t[:n].cpu().numpy()
+    want = oracle.synth_fixed(n, 150, off)
+    np.testing.assert_array_equal(got, want)
+    if off % 321 == 0:
+        check_device_vs_oracle(torch, oracle, eng, want.tobytes())
+
+
+def test_synth_fixed_unaligned_window(torch, oracle, eng):
+    # a window that starts and ends mid-record
+    n, off = 100003, 777
+    t = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    eng.synth_fixed(t, n, byte_off=off)
+    np.testing.assert_array_equal(t[:n].cpu().numpy(), oracle.synth_fixed(n, 150, off))
+
+
+@pytest.mark.parametrize("n_rec,first", [(1, 0), (2000, 0), (30000, 987654321)])
+def test_synth_var_generator_and_parse(n_rec, first, torch, oracle, eng300):
+    t, total = eng300.synth_var(n_rec, first=first, pad=64)
+    want = oracle.synth_var(n_rec, first)
+    assert total == want.size
+    np.testing.assert_array_equal(t[:total].cpu().numpy(), want)
+    check_device_vs_oracle(torch, oracle, eng300, want.tobytes())
+
+
+def test_var_length_with_small_P(torch, oracle, eng):
+    # variable 50..300 bp reads against P = 150: clipping + len_hist overflow bin
+    want = oracle.synth_var(5000, 0)
+    check_device_vs_oracle(torch, oracle, eng, want.tobytes())
+
+
+def test_crlf_synthetic(torch, oracle, eng):
+    data = b"".join(_rec(i, 150, crlf=True) for i in range(400))
+    check_device_vs_oracle(torch, oracle, eng, data)
+
+
+def test_count_lines(torch, oracle, eng):
+    for n in (0, 1, 15, 16, 17, 321 * 1000 + 5):
+        data = oracle.synth_fixed(n, 150, 0).tobytes()
+        t = to_dev(torch, data)
+        assert eng.count_lines(t, n) == data.count(b"\n")
+
+
+# --------------------------------------------------------------------------------------------
+# error in the middle of a large input: everything before the first bad record is delivered
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["header", "sep", "length", "truncated"])
+def test_error_mid_stream(kind, torch, oracle, eng):
+    n_rec = 4000
+    a = bytearray(oracle.synth_fixed_records(n_rec).tobytes())
+    k = 2500
+    base = k * 321
+    if kind == "header":
+        a[base] = ord("X")
+    elif kind == "sep":
+        a[base + 17 + 151] = ord("-")
+    elif kind == "length":
+        a[base + 17 + 151 + 2 + 10] = ord("\n")   # splits the quality line
+    elif kind == "truncated":
+        a = a[:base + 200]
+    out, st = check_device_vs_oracle(torch, oracle, eng, bytes(a))
+    assert out.n_records == k and out.status != 0
+
+
+# --------------------------------------------------------------------------------------------
+# shards: cut a small stream at EVERY byte; owner = shard where the record starts
+# --------------------------------------------------------------------------------------------
+def test_two_shards_every_cut(torch, oracle, eng):
+    data = (b"@a\nACGT\n+\n!!!!\n@bb\nNN\n+x\n##\n@c\n\n+\n\n@dddd\nACGTACGTAC\n+\n@+@+@+@+@+\n")
+    P = eng.max_len
+    _, ost = oracle.each_stats(data, P)
+    n = len(data)
+    for cut in range(0, n + 1):
+        # shard 0 = [0, cut) with the rest as halo; shard 1 = [cut, n) in its own 16-B aligned buffer
+        t0 = to_dev(torch, data)
+        eng.parse_device(t0, n_own=cut, n_avail=n, line_start=True, eof=True)
+        o0, s0 = eng.fetch()
+        lines0 = data[:cut].count(b"\n")
+        assert o0.n_lines == lines0
+        buf1 = torch.zeros(16 + (n - cut) + 64, dtype=torch.uint8, device="cuda")
+        front = data[max(0, cut - 16):cut]
+        if front:
+            buf1[16 - len(front):16] = torch.from_numpy(np.frombuffer(front, dtype=np.uint8).copy())
+        if n - cut:
+            buf1[16:16 + n - cut] = torch.from_numpy(np.frombuffer(data[cut:], dtype=np.uint8).copy())
+        eng.parse_device(buf1[16:], n_own=n - cut, n_avail=n - cut, line_base=lines0,
+                         stream_offset=cut, line_start=(cut == 0), front16=(cut > 0), eof=True)
+        o1, s1 = eng.fetch()
+        assert o0.status == 0 and o1.status == 0, (cut, o0, o1)
+        assert o0.n_records + o1.n_records == ost.n_records, cut
+        np.testing.assert_array_equal(s0.words + s1.words, _oracle_words(eng, ost), err_msg=f"cut={cut}")
+
+
+def _oracle_words(engine, ost):
+    from fastq_rs_b200 import _lib
+    L = _lib.lib()
+    P = engine.max_len
+    w = np.zeros(L.fqb_stats_words(P), dtype=np.uint64)
+    w[0], w[1], w[2], w[3] = ost.n_records, ost.n_bases, ost.clip_seq, ost.clip_qual
+    lo, bo, qo = L.fqb_stats_len_hist_off(P), L.fqb_stats_base_hist_off(P), L.fqb_stats_qual_hist_off(P)
+    w[lo:lo + P + 2] = ost.len_hist
+    w[bo:bo + 6 * P] = ost.base_hist.reshape(-1)
+    w[qo:qo + 256 * P] = ost.qual_hist.reshape(-1)
+    return w
+
+
+def test_shards_synthetic_unaligned_cuts(torch, oracle, eng):
+    # 4 shards of a 3 MB synthetic stream, cuts mid-record; halo = head of the next shard
+    n = 321 * 9000
+    data = oracle.synth_fixed(n, 150, 0).tobytes()
+    _, ost = oracle.each_stats(data, eng.max_len)
+    cuts = [0, 700001, 1500016, 2200333, n]
+    total = np.zeros_like(_oracle_words(eng, ost))
+    nrec = 0
+    full = to_dev(torch, data)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        a16 = a & ~15  # device buffers must be 16-byte aligned: shard view starts at an aligned address
+        # emulate an aligned private copy: [front16 | shard | halo]
+        buf = torch.zeros(16 + (n - a) + 64, dtype=torch.uint8, device="cuda")
+        lo = max(0, a - 16)
+        buf[16 - (a - lo):16 + (n - a)] = full[lo:n]
+        halo = min(n - b, 68 * 1024)
+        eng.parse_device(buf[16:], n_own=b - a, n_avail=b - a + halo, line_base=data[:a].count(b"\n"),
+                         stream_offset=a, line_start=(a == 0), front16=(a > 0), eof=(b + halo == n))
+        o, s = eng.fetch()
+        assert o.status == 0
+        nrec += o.n_records
+        total += s.words
+        del a16
+    assert nrec == ost.n_records
+    np.testing.assert_array_equal(total, _oracle_words(eng, ost))
+
+
+# --------------------------------------------------------------------------------------------
+# streaming ring: chunk boundaries, short fills, errors in later chunks
+# --------------------------------------------------------------------------------------------
+def test_streaming_small_slots(fq, oracle):
+    e = fq.Engine(max_len=150, slot_bytes=2 * 68 * 1024, n_slots=2)
+    try:
+        data = oracle.synth_fixed_records(9000).tobytes()   # ~2.9 MB -> 21 chunks
+        _, ost = oracle.each_stats(data, 150)
+        out, st, idx = e.parse_host(data, want_index=True)
+        assert out.status == 0 and out.n_records == 9000
+        assert_stats_equal(st, ost)
+        _, oidx = oracle.each_index(data)
+        np.testing.assert_array_equal(idx.reshape(-1, 4), oidx[:, 1:5])
+        # acquire/submit protocol with short, ragged fills (a reader that returns short reads)
+        e.stream_begin()
+        pos, k = 0, 0
+        while pos < len(data):
+            slot = e.stream_acquire()
+            take = min(len(slot), len(data) - pos, 1 + (k * 7919) % 50000)
+            np.frombuffer(slot, dtype=np.uint8)[:take] = np.frombuffer(data[pos:pos + take], dtype=np.uint8)
+            e.stream_submit(take)
+            pos += take
+            k += 1
+        out2, st2 = e.stream_finish()
+        assert out2.status == 0 and out2.n_records == 9000
+        assert_stats_equal(st2, ost)
+        # an error in a late chunk: counts stop exactly at the bad record
+        bad = bytearray(data)
+        bad[7000 * 321] = ord("X")
+        ores, ost_b = oracle.each_stats(bytes(bad), 150)
+        out3, st3, _ = e.parse_host(bytes(bad))
+        assert (out3.status, out3.n_records, out3.err_offset) == (ores.status, 7000, ores.err_offset)
+        assert_stats_equal(st3, ost_b)
+        # truncated at the very end
+        out4, st4, _ = e.parse_host(data[:-1])
+        ores4, ost4 = oracle.each_stats(data[:-1], 150)
+        assert (out4.status, out4.n_records) == (ores4.status, ores4.n_records)
+        assert_stats_equal(st4, ost4)
+        # record that straddles a chunk boundary while being longer than the tile halo
+        big = b"".join(_rec(i, L) for i, L in enumerate([60000, 150, 60000, 30000, 150, 65000, 10] * 3))
+        ores5, ost5 = oracle.each_stats(big, 150)
+        out5, st5, _ = e.parse_host(big)
+        assert (out5.status, out5.n_records) == (ores5.status, ores5.n_records)
+        assert_stats_equal(st5, ost5)
+    finally:
+        e.close()
+
+
+# --------------------------------------------------------------------------------------------
+# property test: random valid FASTQ, randomly mutated (reference fuzz targets, fuzz/fuzz_targets/*.rs)
+# --------------------------------------------------------------------------------------------
+def test_hypothesis_mutations(torch, oracle, eng):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(0, 2**32 - 1), st.integers(1, 60), st.integers(0, 4))
+    def run(seed, n_rec, n_mut):
+        rng = np.random.default_rng(seed)
+        recs = []
+        for i in range(n_rec):
+            L = int(rng.integers(0, 40)) if rng.random() < 0.8 else int(rng.integers(100, 400))
+            recs.append(_rec(int(rng.integers(0, 1 << 30)), L, crlf=bool(rng.random() < 0.2)))
+        data = bytearray(b"".join(recs))
+        for _ in range(n_mut):
+            if not data:
+                break
+            p = int(rng.integers(0, len(data)))
+            op = rng.integers(0, 4)
+            if op == 0:
+                data[p] = int(rng.integers(0, 256))
+            elif op == 1:
+                del data[p]
+            elif op == 2:
+                data.insert(p, int(rng.choice([10, 13, 43, 64, 65])))
+            else:
+                data = data[:p]
+        check_device_vs_oracle(torch, oracle, eng, bytes(data))
+
+    run()
+
+
+# --------------------------------------------------------------------------------------------
+# scale: 1 GiB synthetic stream, size-independent properties (count, checksums) + oracle on a prefix
+# --------------------------------------------------------------------------------------------
+def test_large_synthetic_properties(torch, oracle, eng):
+    n_rec = 3_000_000          # ~0.96 GB
+    n = n_rec * 321
+    t = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    eng.synth_fixed(t, n)
+    idx = torch.empty(4 * n_rec + 8, dtype=torch.int32, device="cuda")
+    eng.parse_device(t, n_own=n, n_avail=n, index=idx)
+    out, st = eng.fetch()
+    assert out.status == 0 and out.n_records == n_rec and out.n_lines == 4 * n_rec
+    assert st.n_bases == 150 * n_rec
+    # every position sees every record exactly once, in both histograms
+    assert (st.base_hist.sum(axis=1) == n_rec).all() and (st.qual_hist.sum(axis=1) == n_rec).all()
+    assert st.len_hist[150] == n_rec
+    # offsets are an arithmetic progression for fixed-length records: closed form check of all of them
+    got = idx[:4 * n_rec].view(n_rec, 4).to(torch.int64) & 0xFFFFFFFF
+    rec0 = torch.arange(n_rec, device="cuda", dtype=torch.int64) * 321
+    for k, rel in enumerate((16, 167, 169, 320)):
+        assert torch.equal(got[:, k], (rec0 + rel) & 0xFFFFFFFF)
+    # oracle on the first 40 000 records must match the histogram of the same prefix
+    m = 40_000
+    eng.parse_device(t, n_own=m * 321, n_avail=m * 321)
+    out2, st2 = eng.fetch()
+    _, ost = oracle.each_stats(t[:m * 321].cpu().numpy(), 150)
+    assert_stats_equal(st2, ost)
