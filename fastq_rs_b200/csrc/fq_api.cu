@@ -236,7 +236,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     if (sh->n_avail && (!sh->d_bytes || (reinterpret_cast<uintptr_t>(sh->d_bytes) & 15))) return FQB_E_ARG;
     if ((sh->flags & FQB_F_INDEX) && sh->index_cap && !sh->d_index) return FQB_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t ntiles64 = (sh->n_own + TILE - 1) / TILE;
+    const uint64_t tile_bytes = scan_tile_bytes(ctx->nchunk);
+    const uint64_t ntiles64 = (sh->n_own + tile_bytes - 1) / tile_bytes;
     if (ntiles64 > 0xFFFFFFF0ull) return FQB_E_ARG;
     if (ntiles64 > ctx->status_cap) {
         if (ctx->d_status) {

@@ -11,18 +11,10 @@
 
 namespace fq {
 
-constexpr int THREADS = 512;               // 16 warps per CTA
-constexpr int NWARPS = THREADS / 32;
-constexpr int TILE = 16384;                // owned bytes per tile
 constexpr int HALO = 1024;                 // bytes staged after the tile (tails of records that start in it)
 constexpr int FRONT = 16;                  // bytes staged before the tile (only the last one matters)
-constexpr int SM_TILE = FRONT + TILE + HALO;
 constexpr int UNIT = 512;                  // one warp x 16 B
-constexpr int NUNITS = (TILE + HALO) / UNIT;
-constexpr int ITERS = (NUNITS + NWARPS - 1) / NWARPS;
-constexpr int LIST_CAP = 4096;             // newline positions kept in shared memory per tile
 constexpr int HIST_ROWS = 128;             // byte values with a shared-memory counter row (ASCII)
-constexpr int CHUNK_WORDS = HIST_ROWS * 32;  // one 32-position chunk: [byte][lane] u32 (lo16 seq, hi16 qual)
 constexpr uint32_t MAXREC = 68u * 1024u;   // src/lib.rs:129 BUFSIZE
 constexpr unsigned long long NONE64 = ~0ull;
 
@@ -80,6 +72,7 @@ __host__ __device__ inline size_t stats_words(uint32_t P) { return 8 + (size_t)P
 
 // launchers (fq_kernels.cu)
 size_t scan_smem_bytes(int nchunk);
+uint32_t scan_tile_bytes(int nchunk);
 cudaError_t scan_configure();
 int scan_blocks_per_sm(int nchunk);
 cudaError_t launch_scan(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
