@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -67,6 +68,8 @@ struct fqb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     uint64_t launches = 0;
+    unsigned long long* d_trace = nullptr;  // FQB_TRACE=<file>: kernel timeline, dumped by fqb_fetch
+    std::string trace_path;
     uint64_t last_off = 0;
     std::string err;
     // streaming
@@ -177,6 +180,10 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(cudaHostAlloc(&ctx->h_res, sizeof(DevResult), cudaHostAllocDefault));
     CKC(cudaHostAlloc(&ctx->h_linecount, 8, cudaHostAllocDefault));
     CKC(cudaHostAlloc(&ctx->h_carry, sizeof(DevCarry), cudaHostAllocDefault));
+    if (const char* tp = getenv("FQB_TRACE")) {
+        ctx->trace_path = tp;
+        CKC(cudaMalloc(&ctx->d_trace, (size_t)ctx->num_sms * TRACE_K * 16 * 8));
+    }
     CKC(cudaEventCreate(&ctx->ev0));
     CKC(cudaEventCreate(&ctx->ev1));
 #undef CKC
@@ -218,6 +225,7 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_status);
     cudaFree(ctx->d_linecount);
     cudaFree(ctx->d_carry);
+    cudaFree(ctx->d_trace);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->h_linecount) cudaFreeHost(ctx->h_linecount);
     if (ctx->h_carry) cudaFreeHost(ctx->h_carry);
@@ -268,6 +276,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.res = ctx->d_res;
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
     p.seqraw = reinterpret_cast<unsigned long long*>(ctx->d_seqraw);
+    p.trace = ctx->d_trace;
+    if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
     fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, ctx->d_ticket);
     CK(cudaGetLastError());
@@ -286,6 +296,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         CK(launch_rerun_reset(p, st));
         ScanParams p2 = p;
         p2.flags |= F_RERUN;
+        p2.trace = nullptr;
         CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
         ctx->launches += 4;
     }
@@ -319,6 +330,14 @@ int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
     CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, st));
     if (host_stats) CK(cudaMemcpyAsync(host_stats, ctx->d_stats, ctx->nwords * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->d_trace) {
+        std::vector<unsigned long long> h((size_t)ctx->num_sms * TRACE_K * 16);
+        CK(cudaMemcpy(h.data(), ctx->d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(ctx->trace_path.c_str(), "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+    }
     fill_result(ctx->h_res, ctx->last_off, res);
     return FQB_OK;
 }

@@ -63,7 +63,9 @@ struct ScanParams {
     DevResult* res;
     unsigned long long* stats;      // stats block
     unsigned long long* seqraw;     // [P][256] raw byte histogram of the sequence lines
+    unsigned long long* trace;      // debug timeline (FQB_TRACE), normally null: [cta][TRACE_K][16] clock64 stamps
 };
+constexpr int TRACE_K = 2048;
 
 __host__ __device__ inline size_t stats_len_off(uint32_t) { return 8; }
 __host__ __device__ inline size_t stats_base_off(uint32_t P) { return 8 + (size_t)P + 2; }

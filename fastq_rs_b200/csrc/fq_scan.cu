@@ -1,19 +1,25 @@
-// fq_scan.cu -- the fused sm_100a scan kernel (K1 delimit + K2 per-position histograms).
+// fq_scan.cu -- the fused sm_100a scan kernel (K1 delimit + K2 per-position histograms), v5.
 //
-// One pass over the bytes.  Persistent grid, one 1024-thread CTA per SM, split into TEAMS
-// independent teams that share one shared-memory histogram.  Every team runs a software
-// pipeline over its statically assigned tiles (tile = team + k * n_teams); in iteration k
+// One pass over the bytes.  Persistent grid, one 1024-thread CTA per SM, static tile schedule
+// (tile = cta + k * grid).  The 32 warps of a CTA are SPECIALISED and hand tiles to each other
+// through a ring of NSTAGE shared-memory stages guarded by mbarriers -- no CTA-wide barrier in the
+// steady state:
 //
-//   control warp   issues the TMA bulk copy of tile k+NBUF-1 (UBLKCP + mbarrier), then resolves
-//                  the line number of tile k with a decoupled look-back over the newline counts
-//                  the other teams published ONE ITERATION EARLIER (so it never waits for a
-//                  team that runs in lock step with this one)
-//   scan(k+1)      other warps: 16-byte SWAR newline masks -> per-unit counts -> ranks ->
-//                  position list of tile k+1; its count is published for the look-backs to come
-//   records(k)     all warps, 8 lanes per record: '@' / '+' / raw-length validation
-//                  (src/records.rs:201-247), then each lane walks 4-byte groups of the sequence
-//                  and quality lines and bumps hist[byte][position] -- bank = position % 32, and
-//                  the (group, byte) rotation makes the 32 lanes of every ATOMS hit 32 banks
+//   TMA warp (1)       keeps the ring full: UBLKCP bulk copies completing on full[s]
+//   look-back warp (1) resolves the stream line number of every tile with a decoupled look-back over
+//                      the newline counts the other CTAs publish; runs concurrently with the scan
+//   scan warps (SW)    16-byte SWAR newline masks (3 ops / word + dp4a bit gather) -> per-unit counts
+//                      -> ranks -> position list of the tile (u16, shared memory); publish the tile's
+//                      newline count for the look-backs of the other CTAs
+//   record warps (HW)  8 lanes per record: '@' / '+' / raw-length validation
+//                      (src/records.rs:201-247), then each lane walks 4-byte groups of the sequence
+//                      and quality lines and bumps hist[chunk][byte][position % 32] with one dp4a
+//                      (address = lane base + byte * 128) and one ATOMS per byte; bank = position % 32
+//                      and the (group, byte) rotation make the 32 lanes of every ATOMS hit 32 banks.
+//                      They also copy the line-end list to the global index.
+//
+//   full[s]    TMA -> scan + look-back      scanned[s]  scan warps -> look-back + record warps
+//   based[s]   look-back -> record warps    freed[s]    record warps + look-back -> TMA warp
 //
 // Reference behaviour reproduced: see fq_kernels.cu header.
 #include "fq_common.cuh"
@@ -21,33 +27,34 @@
 
 namespace fq {
 
-template <int NCHUNK_, int TEAMS_, int TILE_, int NBUF_>
+template <int NCHUNK_, int TILE_, int NSTAGE_, int SCANW_>
 struct Cfg {
-    static constexpr int NCHUNK = NCHUNK_, TEAMS = TEAMS_, TILE = TILE_, NBUF = NBUF_;
+    static constexpr int NCHUNK = NCHUNK_, TILE = TILE_, NSTAGE = NSTAGE_;
+    static constexpr int SW = SCANW_;                      // scan warps
+    static constexpr int HW = 30 - SCANW_;                 // record / histogram warps (warps 0, 1: TMA, look-back)
     static constexpr int PPAD = 32 * NCHUNK;               // positions with a shared-memory counter column
-    static constexpr int TW = 32 / TEAMS;                  // warps per team
-    static constexpr int TT = TW * 32;                     // threads per team
-    static constexpr int SW = TW - 1;                      // warps that scan (warp 0 is the control warp)
     static constexpr int SM_TILE = FRONT + TILE + HALO;
     static constexpr int TILE_PAD = (SM_TILE + 16 + 127) / 128 * 128;
     static constexpr int NUNITS = (TILE + HALO) / UNIT;
     static constexpr int OWN_UNITS = TILE / UNIT;
     static constexpr int ITERS = (NUNITS + SW - 1) / SW;
     static constexpr int UPL = (NUNITS + 31) / 32;         // unit counts per lane
-    static constexpr int LIST_CAP = TILE / 4;
-    static constexpr int HIST_WORDS = HIST_ROWS * PPAD;    // hist[byte][position], u32 = lo16 seq | hi16 qual
+    static constexpr int LIST_CAP = TILE / 8;              // line ends the position list holds
+    static constexpr int LIST_DUMMY = LIST_CAP + 16;       // writes beyond the capacity land here
+    static constexpr int LIST_BYTES = (LIST_CAP * 2 + 64 + 127) / 128 * 128;
+    static constexpr int CHUNK_WORDS = HIST_ROWS * 32;     // one 32-position chunk: [byte][32] u32
+    static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;   // u32 = lo16 seq | hi16 qual
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
-    static constexpr int TEAM_BYTES = NBUF * TILE_PAD + 2 * LIST_CAP * 2;
     // word loads of the record pass may run up to PPAD + 8 bytes past a tile buffer: keep them inside
     static constexpr int TAIL_PAD = (PPAD + 8 + 127) / 128 * 128;
-    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + TEAMS * TEAM_BYTES + TAIL_PAD;
-    static constexpr uint32_t ROW_BYTES = PPAD * 4;
+    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + NSTAGE * (TILE_PAD + LIST_BYTES) + TAIL_PAD;
     static_assert(SM_TILE < 65536, "list entries are u16");
-    static_assert(UPL <= 3, "unit counts: <= 96 units");
+    static_assert(UPL <= 2, "unit counts: <= 64 units");
+    static_assert(SW >= 1 && HW >= 1, "roles");
 };
 
 struct TileMeta {
-    unsigned long long base;   // stream-global exclusive line count at the tile start
+    unsigned long long base;   // stream-global exclusive line count at the tile start (control warp)
     unsigned long long ts;     // buffer-relative offset of the tile
     uint32_t front;            // 1 if the byte before the tile is (or acts as) '\n'
     uint32_t own_count;        // '\n' in the owned range
@@ -55,26 +62,30 @@ struct TileMeta {
     uint32_t own_len;
 };
 
-template <int NBUF, int NUNITS>
-struct TeamCtl {
-    unsigned long long full[NBUF];   // mbarriers: tile bytes landed
-    TileMeta meta[2];
-    uint32_t unit_all[2][NUNITS + 2];
+template <int NUNITS>
+struct StageCtl {
+    unsigned long long full;      // mbarrier: tile bytes landed (TMA)
+    unsigned long long scanned;   // mbarrier: position list + meta complete (SW arrivals)
+    unsigned long long based;     // mbarrier: meta.base known (control warp)
+    unsigned long long freed;     // mbarrier: stage may be overwritten (HW + 1 arrivals)
+    TileMeta meta;
+    uint32_t unit_all[NUNITS + 2];
     uint32_t unit_own[NUNITS + 2];
-    uint32_t pass_counter[2];   // records(k) hands out passes from pass_counter[k & 1]
-    int nonascii_iter[2];       // == k + 1 when tile k holds a byte >= 0x80
-    int flush_iter;             // iteration at whose end this team drains the shared counters
-    uint32_t pad;
+    uint32_t nonascii;            // tile holds a byte >= 0x80
 };
 
 struct CtaCtl {
     uint32_t recs_since_flush;
+    uint32_t flush_epoch;
 };
 
-template <int NTHREADS>
-__device__ __forceinline__ void team_bar(int team)
+__device__ __forceinline__ void named_bar(int id, int nthreads)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(NTHREADS) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int OFF>
@@ -87,23 +98,59 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 template <int OFF>
 __device__ __forceinline__ void red_add(uint32_t addr, uint32_t v)
 {
-    asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v));
+}
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// debug timeline: one clock64 stamp per (tile, event); no-op unless the host set p.trace (FQB_TRACE)
+__device__ __forceinline__ void trace_ev(const ScanParams& p, int k, int ev, bool use_max = false)
+{
+    if (p.trace && k < TRACE_K) {
+        unsigned long long* slot = p.trace + ((size_t)blockIdx.x * TRACE_K + k) * 16 + ev;
+        if (use_max)
+            atomicMax(slot, (unsigned long long)clock64());
+        else
+            *slot = (unsigned long long)clock64();
+    }
+}
+
+// word index of hist[chunk][byte][position % 32]
+template <class C>
+__device__ __forceinline__ uint32_t hist_word(uint32_t byte, uint32_t pos)
+{
+    return (pos >> 5) * (uint32_t)C::CHUNK_WORDS + byte * 32u + (pos & 31u);
+}
+
+// newline mask of a 16-byte piece, shifted left by 7: bit 7 + i = byte i is '\n'
+// (the four 0x80 flags of each word are gathered by dp4a with weights 1,2,4,8 / 16,32,64,128)
+__device__ __forceinline__ uint32_t nlmask16s7(const uint4& v)
+{
+    const uint32_t m0 = nlbits(v.x), m1 = nlbits(v.y), m2 = nlbits(v.z), m3 = nlbits(v.w);
+    const uint32_t lo = dp4a_u(m1, 0x80402010u, dp4a_u(m0, 0x08040201u, 0u));
+    const uint32_t hi = dp4a_u(m3, 0x80402010u, dp4a_u(m2, 0x08040201u, 0u));
+    return lo + (hi << 8);
 }
 
 // ------------------------------------------------------------------------------------------
 // lock-free drain of the u16-pair counters: atomicExch leaves concurrent increments of the other
-// team intact, so a team may flush whenever the CTA-wide record counter says a half could
+// warps intact, so a slice may be flushed whenever the CTA-wide record counter says a half could
 // approach 65535
 // ------------------------------------------------------------------------------------------
 template <class C>
-__device__ void flush_hist(uint32_t* hist, const ScanParams& p, int tid, int nthreads)
+__device__ void flush_hist(uint32_t* hist, const ScanParams& p, int first, int last, int tid, int nthreads)
 {
     const uint32_t P = p.max_len;
     unsigned long long* qual = p.stats + stats_qual_off(P);
-    for (int i = tid; i < C::HIST_WORDS; i += nthreads) {
+    for (int i = first + tid; i < last; i += nthreads) {
         if (hist[i] == 0) continue;
         const uint32_t v = atomicExch(hist + i, 0u);
-        const uint32_t b = (uint32_t)i / C::PPAD, pos = (uint32_t)i % C::PPAD;
+        const uint32_t chunk = (uint32_t)i / C::CHUNK_WORDS, r = (uint32_t)i % C::CHUNK_WORDS;
+        const uint32_t b = r >> 5, pos = chunk * 32u + (r & 31u);
         const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
         if (pos < P) {
             if (lo) atomicAdd(p.seqraw + (size_t)pos * 256 + b, (unsigned long long)lo);
@@ -188,14 +235,14 @@ __device__ __noinline__ unsigned long long record_global(const ScanParams& p, un
         for (uint32_t c = lane; c < ns; c += 32) {
             const uint32_t b = sq[c];
             if (c < Pm && b < (uint32_t)HIST_ROWS)
-                atomicAdd(hist + b * C::PPAD + c, 1u);
+                atomicAdd(hist + hist_word<C>(b, c), 1u);
             else
                 atomicAdd(p.seqraw + (size_t)c * 256 + b, 1ull);
         }
         for (uint32_t c = lane; c < nq; c += 32) {
             const uint32_t b = ql[c];
             if (c < Pm && b < (uint32_t)HIST_ROWS)
-                atomicAdd(hist + b * C::PPAD + c, 0x10000u);
+                atomicAdd(hist + hist_word<C>(b, c), 0x10000u);
             else
                 atomicAdd(qualg + (size_t)c * 256 + b, 1ull);
         }
@@ -215,14 +262,29 @@ __device__ __noinline__ unsigned long long record_global(const ScanParams& p, un
 // lane = 8*sub + i.  In round T lane (sub,i) owns the 4-byte group g = i + 8T of its record's
 // sequence and quality lines and visits its bytes in the order (k + sub) & 3, k = 0..3, so that
 // the k-th ATOMS of the round touches position 4g + ((k+sub)&3): over the 32 lanes these are 32
-// different residues mod 32 = 32 different banks of hist[byte][position].
+// different residues mod 32 = 32 different banks of hist[chunk][byte][position % 32].
 // ------------------------------------------------------------------------------------------
+struct LaneConst {         // fixed per lane for the whole kernel
+    uint32_t hk[4];        // shared address of hist[0][0][pk[k]]
+    uint32_t wsel[4];      // dp4a weights: 128 in the byte lane visited k-th
+    uint32_t pk[4];        // position visited by the k-th bump in round 0
+};
+
+struct TileView {          // warp-uniform view of the tile being consumed
+    const uint8_t* tile;
+    const uint16_t* list;
+    unsigned long long ts;   // buffer-relative offset of the tile
+    uint32_t tile_s;         // shared address of `tile`
+    uint32_t f;              // 1 if list[0] is the line end before the tile
+    uint32_t nown;           // list entries that end a line inside the owned range (+f)
+    uint32_t nstored;        // list entries stored
+    uint32_t j0;             // first list entry after which a record starts
+    uint32_t own_end;        // tile offset of the end of the owned range
+};
+
 struct RoundCtx {
     uint32_t as0, aq0;     // shared addresses of the aligned words holding position 4i of seq / qual
     uint32_t shs, shq;     // funnel shifts that realign them
-    uint32_t rot;          // 8 * sub
-    uint32_t hk[4];        // shared address of hist[0][pk[k]]
-    uint32_t pk[4];        // position visited by the k-th bump in round 0
     uint32_t ns, nq;       // bytes of seq / qual that have a shared-memory column
     uint32_t nmax_w, nmin_w;
     unsigned long long *gseq, *gqual;   // global rows (non-ASCII bytes only)
@@ -230,81 +292,84 @@ struct RoundCtx {
 
 template <class C, bool ASCII, int T>
 struct Rounds {
-    static __device__ __forceinline__ void run(const RoundCtx& c)
+    static __device__ __forceinline__ void run(const RoundCtx& c, const LaneConst& lc)
     {
         if (32u * T >= c.nmax_w) return;                                  // warp-uniform
         const uint32_t s0 = lds32<32 * T>(c.as0), s1 = lds32<32 * T + 4>(c.as0);
         const uint32_t q0 = lds32<32 * T>(c.aq0), q1 = lds32<32 * T + 4>(c.aq0);
-        uint32_t vs = __funnelshift_r(s0, s1, c.shs);
-        uint32_t vq = __funnelshift_r(q0, q1, c.shq);
-        vs = __funnelshift_r(vs, vs, c.rot);                              // byte k = byte (k+sub)&3 of the group
-        vq = __funnelshift_r(vq, vq, c.rot);
+        const uint32_t vs = __funnelshift_r(s0, s1, c.shs);
+        const uint32_t vq = __funnelshift_r(q0, q1, c.shq);
+        constexpr int CO = 4 * C::CHUNK_WORDS * T;                        // byte offset of chunk T
         if (ASCII && 32u * (T + 1) <= c.nmin_w) {                         // every lane's group lies inside both lines
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                red_add<128 * T>(c.hk[k] + __byte_perm(vs, 0, 0x4440 + k) * C::ROW_BYTES, 1u);
-                red_add<128 * T>(c.hk[k] + __byte_perm(vq, 0, 0x4440 + k) * C::ROW_BYTES, 0x10000u);
+                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
+                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t pos = c.pk[k] + 32u * T;
-                const uint32_t bs = __byte_perm(vs, 0, 0x4440 + k), bq = __byte_perm(vq, 0, 0x4440 + k);
+                const uint32_t pos = lc.pk[k] + 32u * T;
                 if (pos < c.ns) {
-                    if (ASCII || bs < (uint32_t)HIST_ROWS)
-                        red_add<128 * T>(c.hk[k] + bs * C::ROW_BYTES, 1u);
-                    else
-                        atomicAdd(c.gseq + (size_t)pos * 256 + bs, 1ull);
+                    if (ASCII) {
+                        red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
+                    } else {
+                        const uint32_t bs = (vs >> (8u * (lc.pk[k] & 3u))) & 0xFFu;
+                        if (bs < (uint32_t)HIST_ROWS)
+                            red_add<CO>(lc.hk[k] + bs * 128u, 1u);
+                        else
+                            atomicAdd(c.gseq + (size_t)pos * 256 + bs, 1ull);
+                    }
                 }
                 if (pos < c.nq) {
-                    if (ASCII || bq < (uint32_t)HIST_ROWS)
-                        red_add<128 * T>(c.hk[k] + bq * C::ROW_BYTES, 0x10000u);
-                    else
-                        atomicAdd(c.gqual + (size_t)pos * 256 + bq, 1ull);
+                    if (ASCII) {
+                        red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
+                    } else {
+                        const uint32_t bq = (vq >> (8u * (lc.pk[k] & 3u))) & 0xFFu;
+                        if (bq < (uint32_t)HIST_ROWS)
+                            red_add<CO>(lc.hk[k] + bq * 128u, 0x10000u);
+                        else
+                            atomicAdd(c.gqual + (size_t)pos * 256 + bq, 1ull);
+                    }
                 }
             }
         }
-        Rounds<C, ASCII, T + 1>::run(c);
+        Rounds<C, ASCII, T + 1>::run(c, lc);
     }
 };
 template <class C, bool ASCII>
 struct Rounds<C, ASCII, C::NCHUNK> {
-    static __device__ __forceinline__ void run(const RoundCtx&) {}
+    static __device__ __forceinline__ void run(const RoundCtx&, const LaneConst&) {}
 };
 
 template <class C, bool ASCII>
-__device__ __forceinline__ void records_pass(const ScanParams& p, const TileMeta& m, const uint8_t* tile,
-                                             const uint16_t* list, uint32_t* hist, uint32_t* lenh,
-                                             unsigned long long limit, uint32_t pass, Acc& acc, int lane)
+__device__ __forceinline__ void records_pass(const ScanParams& p, const TileView& tv, const LaneConst& lc,
+                                             uint32_t* hist, uint32_t* lenh, unsigned long long limit,
+                                             uint32_t pass, Acc& acc, int lane)
 {
     const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
-    const uint32_t f = m.front;
-    const uint32_t nown = f + m.own_count;
-    const uint32_t nstored = min(f + m.total_count, (uint32_t)C::LIST_CAP);
-    const uint32_t gb = (uint32_t)((m.base - f) & 3ull);   // list entry j ends global line (base - f + j)
-    const uint32_t j0 = (3u - gb) & 3u;                     // a record starts after every line = 3 (mod 4)
-    const uint32_t own_end = FRONT + m.own_len;
-    const uint32_t j = j0 + 4u * (4u * pass + sub);
-
-    bool valid = j < nown;
-    uint32_t s = FRONT;
-    if (valid) {
-        s = (uint32_t)list[j] + 1u;
-        valid = s < own_end;                                // else it starts in the next tile
-    }
-    const unsigned long long abs_s = m.ts + s - FRONT;
-    valid = valid && abs_s < limit;
-    const bool complete = valid && (j + 4u < nstored);
-    uint32_t h = FRONT, q = FRONT, pp = FRONT, e = FRONT;
+    const uint8_t* tile = tv.tile;
+    const uint32_t j = tv.j0 + 4u * (4u * pass + sub);
+    // the five line ends around the record, loaded together (entries past the stored ones are stale
+    // values that the predicates below never let through)
+    const uint16_t* lp = tv.list + min(j, (uint32_t)C::LIST_CAP);
+    const uint32_t l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3], l4 = lp[4];
+    const uint32_t s = l0 + 1u;
+    bool valid = j < tv.nown && s < tv.own_end;            // else it starts in the next tile
+    if (limit != NONE64) valid = valid && (tv.ts + s - FRONT) < limit;
+    const bool complete = valid && (j + 4u < tv.nstored);
+    // stale entries must not turn into wild shared-memory addresses in the rounds below
+    const uint32_t h = complete ? l1 : (uint32_t)FRONT, q = l2, pp = complete ? l3 : (uint32_t)FRONT, e = l4;
     bool ok = false;
+    uint32_t c_at = 0, c_plus = 0, c_sr = 0, c_qr = 0;
     if (complete) {
-        h = list[j + 1];
-        q = list[j + 2];
-        pp = list[j + 3];
-        e = list[j + 4];
+        c_at = tile[s];
+        c_plus = tile[q + 1];
+        c_sr = tile[q - 1];
+        c_qr = tile[e - 1];
         // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
-        ok = tile[s] == '@' && tile[q + 1] == '+' && (e - pp) == (q - h);
-        if (!ok && i == 0) atomicMin(&p.res->first_bad, abs_s);
+        ok = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
+        if (!ok && i == 0) atomicMin(&p.res->first_bad, tv.ts + s - FRONT);
     }
     if (ok && i == 0) acc.n_records++;
 
@@ -315,8 +380,8 @@ __device__ __forceinline__ void records_pass(const ScanParams& p, const TileMeta
         if (ok) {
             const uint32_t Lr = q - h - 1u;
             // seq()/qual() drop one trailing '\r' (src/records.rs:65-73,82-90)
-            Ls = Lr - ((Lr > 0 && tile[q - 1] == '\r') ? 1u : 0u);
-            Lq = Lr - ((Lr > 0 && tile[e - 1] == '\r') ? 1u : 0u);
+            Ls = Lr - ((Lr > 0 && c_sr == '\r') ? 1u : 0u);
+            Lq = Lr - ((Lr > 0 && c_qr == '\r') ? 1u : 0u);
             if (i == 0) account_record<C>(acc, lenh, p, Ls, Lq);
         }
         RoundCtx c;
@@ -326,20 +391,13 @@ __device__ __forceinline__ void records_pass(const ScanParams& p, const TileMeta
         c.nmin_w = __reduce_min_sync(0xffffffffu, min(c.ns, c.nq));
         const uint32_t sa = h + 1u + 4u * i;                // shared offset of position 4i of the sequence line
         const uint32_t qa = pp + 1u + 4u * i;
-        const uint32_t tile_s = smem_u32(tile);
-        c.as0 = tile_s + (sa & ~3u);
-        c.aq0 = tile_s + (qa & ~3u);
+        c.as0 = tv.tile_s + (sa & ~3u);
+        c.aq0 = tv.tile_s + (qa & ~3u);
         c.shs = (sa & 3u) * 8u;
         c.shq = (qa & 3u) * 8u;
-        c.rot = 8u * sub;
         c.gseq = p.seqraw;
         c.gqual = p.stats + stats_qual_off(P);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            c.pk[k] = 4u * i + (((uint32_t)k + sub) & 3u);
-            c.hk[k] = smem_u32(hist) + 4u * c.pk[k];
-        }
-        Rounds<C, ASCII, 0>::run(c);
+        Rounds<C, ASCII, 0>::run(c, lc);
         // positions beyond the shared-memory columns but below P: straight to global (P > PPAD only)
         if (P > Pm && ok) {
             const uint32_t gs = min(Ls, P), gq = min(Lq, P);
@@ -353,7 +411,7 @@ __device__ __forceinline__ void records_pass(const ScanParams& p, const TileMeta
     while (slow) {
         const int src = __ffs(slow) - 1;
         slow &= slow - 1;
-        const unsigned long long a = __shfl_sync(0xffffffffu, abs_s, src);
+        const unsigned long long a = __shfl_sync(0xffffffffu, tv.ts + s - FRONT, src);
         record_global<C>(p, a, limit, hist, lenh, lane);
     }
 }
@@ -368,7 +426,7 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
     for (;;) {
         unsigned long long v[4];
         bool ready;
-        do {
+        for (;;) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const long long idx = pos - 32 * r - lane;
@@ -384,7 +442,9 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
                 if (nil & below) ready = false;
                 if (inc || !ready) break;
             }
-        } while (!ready);
+            if (ready) break;
+            __nanosleep(100);   // the predecessors are still scanning: leave the issue slots to the other warps
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const unsigned inc = __ballot_sync(0xffffffffu, (v[r] >> 62) == 2);
@@ -400,14 +460,45 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
     }
 }
 
-// exclusive prefix of the unit counts for unit u (u warp-uniform): f + sum_{u' < u} cnt[u']
-template <int UPL>
-__device__ __forceinline__ uint32_t unit_prefix(const uint32_t (&cnt)[UPL], int u, int lane, uint32_t f)
+// warp-exclusive prefix of small per-lane counts (most are 0, a few 1 or 2): ballot levels
+__device__ __forceinline__ uint32_t small_prefix(int c, uint32_t lt_mask)
 {
-    uint32_t x = 0;
-#pragma unroll
-    for (int r = 0; r < UPL; ++r) x += (lane + 32 * r < u) ? cnt[r] : 0u;
-    return f + __reduce_add_sync(0xffffffffu, x);
+    const unsigned b1 = __ballot_sync(0xffffffffu, c > 0);
+    const unsigned b2 = __ballot_sync(0xffffffffu, c > 1);
+    const unsigned b3 = __ballot_sync(0xffffffffu, c > 2);
+    uint32_t pre = (uint32_t)__popc(b1 & lt_mask) + (uint32_t)__popc(b2 & lt_mask);
+    if (b3) {
+        pre += (uint32_t)__popc(b3 & lt_mask);
+        for (int lvl = 3;; ++lvl) {
+            const unsigned b = __ballot_sync(0xffffffffu, c > lvl);
+            if (!b) break;
+            pre += (uint32_t)__popc(b & lt_mask);
+        }
+    }
+    return pre;
+}
+
+// line ends of the owned range of a dense-newline tile (more than the list holds; never a healthy
+// FASTQ), ranked straight into the index by one warp
+template <class C>
+__device__ __noinline__ void index_dense(const ScanParams& p, const uint8_t* tile, uint32_t own_count,
+                                         unsigned long long idx_base, unsigned long long off_base, int lane)
+{
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t run = 0;
+    for (int u = 0; u < C::OWN_UNITS && run < own_count; ++u) {
+        const uint32_t off = (uint32_t)u * UNIT + (uint32_t)lane * 16u;
+        uint32_t mm = nlmask16s7(*reinterpret_cast<const uint4*>(tile + FRONT + off)) >> 7;
+        uint32_t rank = run + small_prefix(__popc(mm), lt_mask);
+        run += __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm));
+        while (mm) {
+            const uint32_t bit = (uint32_t)__ffs(mm) - 1u;
+            mm &= mm - 1u;
+            if (rank < own_count && idx_base + rank < p.index_cap)
+                p.index[idx_base + rank] = (uint32_t)(off_base + off + bit);
+            ++rank;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -419,18 +510,14 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* lenh = hist + C::HIST_WORDS;
-    __shared__ TeamCtl<C::NBUF, C::NUNITS> ctl_all[C::TEAMS];
+    __shared__ StageCtl<C::NUNITS> stage_ctl[C::NSTAGE];
     __shared__ CtaCtl cta;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int team = tid / C::TT;
-    const int ttid = tid - team * C::TT;          // thread within the team
-    const int warp = ttid >> 5;                   // warp within the team; 0 = control warp
+    const int warp = tid >> 5;                    // 0 = TMA, 1 = look-back, 2..SW+1 = scan, rest = records
     const uint32_t lt_mask = (1u << lane) - 1u;
-    TeamCtl<C::NBUF, C::NUNITS>& ctl = ctl_all[team];
-    uint8_t* team_mem = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4 + team * C::TEAM_BYTES;
-    uint16_t* lists = reinterpret_cast<uint16_t*>(team_mem + C::NBUF * C::TILE_PAD);
+    uint8_t* stage_mem = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4;
 
     unsigned long long limit = NONE64;
     if (p.flags & F_RERUN) {
@@ -441,263 +528,281 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
 
     for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += 1024) hist[i] = 0;
-    if (ttid == 0) {
-        for (int b = 0; b < C::NBUF; ++b) mbar_init(&ctl.full[b], 1);
+    if (tid == 0) {
+        for (int s = 0; s < C::NSTAGE; ++s) {
+            mbar_init(&stage_ctl[s].full, 1);
+            mbar_init(&stage_ctl[s].scanned, C::SW);
+            mbar_init(&stage_ctl[s].based, 1);
+            mbar_init(&stage_ctl[s].freed, C::HW + 1);
+            stage_ctl[s].nonascii = 0;
+        }
         fence_mbar_init();
-        ctl.pass_counter[0] = ctl.pass_counter[1] = 0;
-        ctl.nonascii_iter[0] = ctl.nonascii_iter[1] = -5;
-        ctl.flush_iter = -5;
+        cta.recs_since_flush = 0;
+        cta.flush_epoch = 0;
     }
-    if (tid == 0) cta.recs_since_flush = 0;
     __syncthreads();
 
-    // static schedule: team gt of n_teams handles tiles gt, gt + n_teams, ...
-    const uint32_t n_teams = gridDim.x * C::TEAMS;
-    const uint32_t gt = blockIdx.x * C::TEAMS + team;
+    // static schedule: CTA b of G handles tiles b, b + G, ...
+    const uint32_t G = gridDim.x;
     uint32_t ntiles_eff = p.ntiles;
     if (limit != NONE64) {
         const unsigned long long lt = limit / C::TILE + 1;   // tiles that start below the limit
         if (lt < ntiles_eff) ntiles_eff = (uint32_t)lt;
     }
-    const int K = gt < ntiles_eff ? (int)((ntiles_eff - gt + n_teams - 1) / n_teams) : 0;
-
-    Acc acc = {0, 0, 0, 0};
+    const int K = blockIdx.x < ntiles_eff ? (int)((ntiles_eff - blockIdx.x + G - 1) / G) : 0;
     const bool want_index = (p.flags & F_INDEX) && !(p.flags & F_RERUN) && p.index != nullptr;
 
-    auto tile_no = [&](int k) -> uint32_t { return gt + (uint32_t)k * n_teams; };
-    auto tile_buf = [&](int k) -> uint8_t* { return team_mem + (k % C::NBUF) * C::TILE_PAD; };
+    auto tile_no = [&](int k) -> uint32_t { return blockIdx.x + (uint32_t)k * G; };
+    auto tile_buf = [&](int k) -> uint8_t* { return stage_mem + (k % C::NSTAGE) * (C::TILE_PAD + C::LIST_BYTES); };
+    auto tile_list = [&](int k) -> uint16_t* { return reinterpret_cast<uint16_t*>(tile_buf(k) + C::TILE_PAD); };
 
-    // issue the bulk copy of tile k (one thread); ragged edges are filled by hand before the scan
-    auto issue = [&](int k) {
-        const unsigned long long ts = (unsigned long long)tile_no(k) * C::TILE;
-        const uint32_t data_len = (uint32_t)min((unsigned long long)(C::TILE + HALO), p.n_avail - ts);
-        const uint32_t front = (ts || (p.flags & F_FRONT16)) ? FRONT : 0;
-        const uint32_t bulk = (front + data_len) & ~15u;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&ctl.full[k % C::NBUF], bulk);
-        if (bulk) bulk_g2s(tile_buf(k) + FRONT - front, p.data + ts - front, bulk, &ctl.full[k % C::NBUF]);
-    };
+    Acc acc = {0, 0, 0, 0};
 
-    if (ttid == 0)
-        for (int k = 0; k < K && k < C::NBUF - 1; ++k) issue(k);
-
-    for (int k = -1; k < K; ++k) {
-        const int kn = k + 1;
-        const bool have_next = kn < K;
-        TileMeta& mk = ctl.meta[k & 1];
-        TileMeta& mn = ctl.meta[kn & 1];
-        uint8_t* tile_n = tile_buf(kn);
-        uint16_t* list_n = lists + (kn & 1) * C::LIST_CAP;
-        uint32_t* unit_all_n = ctl.unit_all[kn & 1];
-
-        // tile k+1 geometry
-        uint32_t tn = 0, own_len_n = 0;
-        unsigned long long ts_n = 0;
-        bool ragged_n = false;
-        if (have_next) {
-            tn = tile_no(kn);
-            ts_n = (unsigned long long)tn * C::TILE;
-            own_len_n = (uint32_t)min((unsigned long long)C::TILE, p.n_own - ts_n);
-            const uint32_t data_len = (uint32_t)min((unsigned long long)(C::TILE + HALO), p.n_avail - ts_n);
-            const uint32_t front = (ts_n || (p.flags & F_FRONT16)) ? FRONT : 0;
-            const uint32_t span = front + data_len;
-            ragged_n = span != (uint32_t)C::SM_TILE;
-            if (ragged_n) {
-                // ragged first / last tiles: leading zeros (or the virtual '\n' of a line start), the
-                // bytes the 16-byte-granular bulk copy leaves out, and zero fill -- by the whole team
-                const uint32_t bulk = span & ~15u;
-                const uint8_t* src = p.data + ts_n - front;
-                uint8_t* dst = tile_n + FRONT - front;
-                const bool virt_nl = ts_n == 0 && front == 0 && (p.flags & F_LINE_START);
-                for (uint32_t i = ttid; i < FRONT - front; i += C::TT) tile_n[i] = (virt_nl && i == FRONT - 1) ? '\n' : 0;
-                for (uint32_t i = bulk + ttid; i < span; i += C::TT) dst[i] = src[i];
-                for (uint32_t i = FRONT + data_len + ttid; i < (uint32_t)C::SM_TILE; i += C::TT) tile_n[i] = 0;
-                team_bar<C::TT>(team);
+    if (warp == 0) {
+        // =====================================================================================
+        // TMA warp: one bulk copy per tile; ragged edges are filled by the scan warps
+        // =====================================================================================
+        for (int k = 0; k < K; ++k) {
+            StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
+            if (k >= C::NSTAGE) mbar_wait(&sc.freed, (uint32_t)(k / C::NSTAGE - 1) & 1u);
+            if (lane == 0) {
+                const unsigned long long ts = (unsigned long long)tile_no(k) * C::TILE;
+                const uint32_t data_len = (uint32_t)min((unsigned long long)(C::TILE + HALO), p.n_avail - ts);
+                const uint32_t front = (ts || (p.flags & F_FRONT16)) ? FRONT : 0;
+                const uint32_t bulk = (front + data_len) & ~15u;
+                sc.nonascii = 0;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&sc.full, bulk);
+                if (bulk) bulk_g2s(tile_buf(k) + FRONT - front, p.data + ts - front, bulk, &sc.full);
+                trace_ev(p, k, 0);
             }
+            __syncwarp();
         }
-
-        uint32_t mask[C::ITERS];
-        if (warp == 0) {
-            // =================================================================================
-            // control warp: keep the TMA ring full, resolve the line number of tile k
-            // =================================================================================
-            if (lane == 0 && k >= 0 && k + C::NBUF - 1 < K) issue(k + C::NBUF - 1);   // buffer of tile k-1: free
-            if (k >= 0) {
-                const uint32_t t = tile_no(k);
-                const unsigned long long excl = t == 0 ? line_base : look_back(p.tile_status, t, lane);
-                if (lane == 0) {
-                    mk.base = excl;
-                    if (t) st_volatile_u64(p.tile_status + t, ST_INC | (excl + mk.own_count));
-                    if (t == p.ntiles - 1 && !(p.flags & F_RERUN)) {
-                        p.res->n_lines = excl + mk.own_count - line_base;
-                        p.res->line_end = excl + mk.own_count;
-                    }
+    } else if (warp == 1) {
+        // =====================================================================================
+        // look-back warp: stream line number of every tile, concurrently with its scan
+        // =====================================================================================
+        for (int k = 0; k < K; ++k) {
+            StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
+            const uint32_t par = (uint32_t)(k / C::NSTAGE) & 1u;
+            mbar_wait(&sc.full, par);             // the stage now belongs to tile k
+            const uint32_t t = tile_no(k);
+            if (lane == 0) trace_ev(p, k, 4);
+            const unsigned long long excl = t == 0 ? line_base : look_back(p.tile_status, t, lane);
+            if (lane == 0) sc.meta.base = excl;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sc.based);
+            if (lane == 0) trace_ev(p, k, 5);
+            mbar_wait(&sc.scanned, par);
+            if (lane == 0) {
+                const uint32_t own_count = sc.meta.own_count;
+                if (t) st_volatile_u64(p.tile_status + t, ST_INC | (excl + own_count));
+                if (t == p.ntiles - 1 && !(p.flags & F_RERUN)) {
+                    p.res->n_lines = excl + own_count - line_base;
+                    p.res->line_end = excl + own_count;
                 }
+                mbar_arrive(&sc.freed);
+                trace_ev(p, k, 6);
             }
-        } else if (have_next) {
-            // =================================================================================
-            // scan(k+1), pass 1: newline masks, per-unit counts
-            // =================================================================================
-            mbar_wait(&ctl.full[kn % C::NBUF], (uint32_t)(kn / C::NBUF) & 1u);
+            __syncwarp();
+        }
+    } else if (warp < 2 + C::SW) {
+        // =====================================================================================
+        // scan warps: newline masks -> unit counts -> ranks -> position list
+        // warp sw owns the units [sw * ITERS, (sw + 1) * ITERS) of every tile
+        // =====================================================================================
+        const int sw = warp - 2;
+        const int sthreads = C::SW * 32;
+        const int stid = sw * 32 + lane;
+        const int u0 = sw * C::ITERS;
+        for (int k = 0; k < K; ++k) {
+            StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
+            uint8_t* tile = tile_buf(k);
+            uint16_t* list = tile_list(k);
+            const uint32_t tn = tile_no(k);
+            const unsigned long long ts = (unsigned long long)tn * C::TILE;
+            const uint32_t own_len = (uint32_t)min((unsigned long long)C::TILE, p.n_own - ts);
+            const uint32_t data_len = (uint32_t)min((unsigned long long)(C::TILE + HALO), p.n_avail - ts);
+            const uint32_t front = (ts || (p.flags & F_FRONT16)) ? FRONT : 0;
+            const uint32_t span = front + data_len;
+            mbar_wait(&sc.full, (uint32_t)(k / C::NSTAGE) & 1u);
+            if (stid == 0) trace_ev(p, k, 1);
+            if (span != (uint32_t)C::SM_TILE) {
+                // ragged first / last tiles: leading zeros (or the virtual '\n' of a line start), the
+                // bytes the 16-byte-granular bulk copy leaves out, and zero fill
+                const uint32_t bulk = span & ~15u;
+                const uint8_t* src = p.data + ts - front;
+                uint8_t* dst = tile + FRONT - front;
+                const bool virt_nl = ts == 0 && front == 0 && (p.flags & F_LINE_START);
+                for (uint32_t i = stid; i < FRONT - front; i += sthreads) tile[i] = (virt_nl && i == FRONT - 1) ? '\n' : 0;
+                for (uint32_t i = bulk + stid; i < span; i += sthreads) dst[i] = src[i];
+                for (uint32_t i = FRONT + data_len + stid; i < (uint32_t)C::SM_TILE; i += sthreads) tile[i] = 0;
+                named_bar(1, sthreads);
+            }
+            // ---- pass 1: newline masks, per-unit counts ------------------------------------------
+            uint32_t mask[C::ITERS], call[C::ITERS];
             uint32_t hib = 0;
 #pragma unroll
             for (int it = 0; it < C::ITERS; ++it) {
-                const int u = it * C::SW + (warp - 1);
+                const int u = u0 + it;
                 mask[it] = 0;
+                call[it] = 0;
                 if (u < C::NUNITS) {
                     const uint32_t off = (uint32_t)u * UNIT + (uint32_t)lane * 16u;
-                    const uint4 v = *reinterpret_cast<const uint4*>(tile_n + FRONT + off);
+                    const uint4 v = *reinterpret_cast<const uint4*>(tile + FRONT + off);
                     hib |= v.x | v.y | v.z | v.w;
-                    const uint32_t mm = nlmask16(v);
+                    const uint32_t mm = nlmask16s7(v);
                     mask[it] = mm;
-                    const uint32_t call = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm));
+                    call[it] = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm));
                     uint32_t cown;
-                    if (own_len_n == (uint32_t)C::TILE) {
-                        cown = u < C::OWN_UNITS ? call : 0u;
+                    if (own_len == (uint32_t)C::TILE) {
+                        cown = u < C::OWN_UNITS ? call[it] : 0u;
                     } else {
-                        const int rem = (int)own_len_n - (int)off;
+                        const int rem = (int)own_len - (int)off;
                         const uint32_t ownm = rem >= 16 ? 0xFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
-                        cown = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm & ownm));
+                        cown = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm & (ownm << 7)));
                     }
                     if (lane == 0) {
-                        unit_all_n[u] = call;
-                        ctl.unit_own[u] = cown;
+                        sc.unit_all[u] = call[it];
+                        sc.unit_own[u] = cown;
                     }
                 }
             }
-            if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0) && lane == 0) ctl.nonascii_iter[kn & 1] = kn + 1;
-        }
-        team_bar<C::TT>(team);   // BAR1: unit counts of tile k+1 and the line number of tile k are visible
-
-        if (have_next) {
-            if (warp == 0) {
-                // ---- control warp: describe tile k+1 and publish its count for later look-backs ----
-                mbar_wait(&ctl.full[kn % C::NBUF], (uint32_t)(kn / C::NBUF) & 1u);   // (already complete)
-                const uint32_t f_n = tile_n[FRONT - 1] == '\n' ? 1u : 0u;
+            if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(&sc.nonascii, 1u);
+            named_bar(1, sthreads);   // unit counts of the tile are visible to all scan warps
+            if (stid == 0) trace_ev(p, k, 2);
+            // ---- totals, published for the look-backs of the other CTAs ---------------------------
+            const uint32_t f = tile[FRONT - 1] == '\n' ? 1u : 0u;
+            uint32_t cnt[C::UPL];
+#pragma unroll
+            for (int r = 0; r < C::UPL; ++r) cnt[r] = (lane + 32 * r) < C::NUNITS ? sc.unit_all[lane + 32 * r] : 0u;
+            if (sw == 0) {
                 uint32_t a = 0, o = 0;
 #pragma unroll
                 for (int r = 0; r < C::UPL; ++r) {
-                    const int u = lane + 32 * r;
-                    a += u < C::NUNITS ? unit_all_n[u] : 0u;
-                    o += u < C::NUNITS ? ctl.unit_own[u] : 0u;
+                    a += cnt[r];
+                    o += (lane + 32 * r) < C::NUNITS ? sc.unit_own[lane + 32 * r] : 0u;
                 }
-                const uint32_t total_n = __reduce_add_sync(0xffffffffu, a);
-                const uint32_t own_count_n = __reduce_add_sync(0xffffffffu, o);
+                const uint32_t total = __reduce_add_sync(0xffffffffu, a);
+                const uint32_t own_count = __reduce_add_sync(0xffffffffu, o);
                 if (lane == 0) {
-                    mn.ts = ts_n;
-                    mn.front = f_n;
-                    mn.own_count = own_count_n;
-                    mn.total_count = total_n;
-                    mn.own_len = own_len_n;
-                    if (f_n) list_n[0] = FRONT - 1;
+                    sc.meta.ts = ts;
+                    sc.meta.front = f;
+                    sc.meta.own_count = own_count;
+                    sc.meta.total_count = total;
+                    sc.meta.own_len = own_len;
+                    if (f) list[0] = FRONT - 1;
                     if (tn == 0)
-                        st_volatile_u64(p.tile_status, ST_INC | (line_base + own_count_n));
+                        st_volatile_u64(p.tile_status, ST_INC | (line_base + own_count));
                     else
-                        st_volatile_u64(p.tile_status + tn, ST_AGG | own_count_n);
-                    ctl.pass_counter[kn & 1] = 0;   // used by records(k+1), after BAR2
-                }
-            } else {
-                // ---- scan(k+1), pass 2: rank every newline, fill the position list ---------------
-                const uint32_t f_n = tile_n[FRONT - 1] == '\n' ? 1u : 0u;
-                uint32_t cnt[C::UPL];
-#pragma unroll
-                for (int r = 0; r < C::UPL; ++r) cnt[r] = (lane + 32 * r) < C::NUNITS ? unit_all_n[lane + 32 * r] : 0u;
-#pragma unroll
-                for (int it = 0; it < C::ITERS; ++it) {
-                    const int u = it * C::SW + (warp - 1);
-                    if (u < C::NUNITS) {
-                        uint32_t mm = mask[it];
-                        const int c = __popc(mm);
-                        int pre = 0;
-                        for (int lvl = 0;; ++lvl) {
-                            const unsigned b = __ballot_sync(0xffffffffu, c > lvl);
-                            if (!b) break;
-                            pre += __popc(b & lt_mask);
-                        }
-                        uint32_t rank = unit_prefix<C::UPL>(cnt, u, lane, f_n) + (uint32_t)pre;
-                        const uint32_t pos0 = FRONT + (uint32_t)u * UNIT + (uint32_t)lane * 16u;
-                        while (mm) {
-                            const uint32_t bit = (uint32_t)__ffs(mm) - 1u;
-                            mm &= mm - 1u;
-                            if (rank < (uint32_t)C::LIST_CAP) list_n[rank] = (uint16_t)(pos0 + bit);
-                            ++rank;
-                        }
-                    }
+                        st_volatile_u64(p.tile_status + tn, ST_AGG | own_count);
                 }
             }
+            // ---- pass 2: rank every newline, fill the position list --------------------------------
+            uint32_t x = 0;
+#pragma unroll
+            for (int r = 0; r < C::UPL; ++r) x += (lane + 32 * r < u0) ? cnt[r] : 0u;
+            uint32_t ubase = f + __reduce_add_sync(0xffffffffu, x);   // rank of the first newline of unit u0
+#pragma unroll
+            for (int it = 0; it < C::ITERS; ++it) {
+                const int u = u0 + it;
+                if (u < C::NUNITS) {
+                    const uint32_t mm = mask[it];                     // bit 7 + i = byte i
+                    const int c = __popc(mm);
+                    const uint32_t rank = ubase + small_prefix(c, lt_mask);
+                    const uint32_t pos0 = FRONT + (uint32_t)u * UNIT + (uint32_t)lane * 16u - 7u;
+                    // the first and the last newline of the piece, no loop; a third one is rare
+                    if (c > 0) list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos0 + (uint32_t)__ffs(mm) - 1u);
+                    if (c > 1) list[min(rank + (uint32_t)c - 1u, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos0 + 31u - (uint32_t)__clz(mm));
+                    if (__any_sync(0xffffffffu, c > 2) && c > 2) {
+                        uint32_t m2 = mm & (mm - 1u), r2 = rank + 1u;
+                        while (m2 & (m2 - 1u)) {
+                            list[min(r2, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos0 + (uint32_t)__ffs(m2) - 1u);
+                            m2 &= m2 - 1u;
+                            ++r2;
+                        }
+                    }
+                    ubase += call[it];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sc.scanned);
+            if (stid == 0) trace_ev(p, k, 3);
+            if (lane == 0) trace_ev(p, k, 10, true);
         }
-
+    } else {
         // =====================================================================================
-        // records(k): index copy, then passes handed out dynamically inside the team
+        // record warps: validation + per-position histograms + index copy; the items of a tile
+        // (record passes, then one index item) are dealt round-robin, rotated from tile to tile
         // =====================================================================================
-        if (k >= 0) {
-            const uint8_t* tile = tile_buf(k);
-            const uint16_t* list = lists + (k & 1) * C::LIST_CAP;
-            const uint32_t f = mk.front, own_count = mk.own_count;
-            const bool overflow = f + mk.total_count > (uint32_t)C::LIST_CAP;
-            const unsigned long long idx_base = mk.base - line_base;     // buffer-local number of the first own line
-            const unsigned long long off_base = p.stream_offset + mk.ts;
-            const uint32_t gb = (uint32_t)((mk.base - f) & 3ull);
-            const uint32_t j0 = (3u - gb) & 3u;
-            const uint32_t nown = f + own_count;
-            const uint32_t nrec = nown > j0 ? (nown - j0 + 3u) / 4u : 0u;
+        const int hw = warp - 2 - C::SW;
+        uint32_t my_epoch = 0;
+        constexpr int SLICE = (C::HIST_WORDS + C::HW - 1) / C::HW;
+        LaneConst lc;
+        {
+            const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
+                lc.pk[kk] = 4u * i + bytek;
+                lc.hk[kk] = smem_u32(hist) + 4u * lc.pk[kk];
+                lc.wsel[kk] = 128u << (8u * bytek);
+            }
+        }
+        for (int k = 0; k < K; ++k) {
+            StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
+            const uint32_t par = (uint32_t)(k / C::NSTAGE) & 1u;
+            mbar_wait(&sc.scanned, par);
+            mbar_wait(&sc.based, par);
+            if (hw == 0 && lane == 0) trace_ev(p, k, 7);
+            const TileMeta mk = sc.meta;
+            TileView tv;
+            tv.tile = tile_buf(k);
+            tv.list = tile_list(k);
+            tv.ts = mk.ts;
+            tv.tile_s = smem_u32(tv.tile);
+            tv.f = mk.front;
+            tv.nown = mk.front + mk.own_count;
+            tv.nstored = min(mk.front + mk.total_count, (uint32_t)C::LIST_CAP);
+            tv.j0 = (3u - (uint32_t)((mk.base - mk.front) & 3ull)) & 3u;   // entry j ends global line base - f + j
+            tv.own_end = FRONT + mk.own_len;
+            const bool overflow = mk.front + mk.total_count > (uint32_t)C::LIST_CAP;
+            const uint32_t nrec = tv.nown > tv.j0 ? (tv.nown - tv.j0 + 3u) / 4u : 0u;
             const uint32_t npass = (nrec + 3u) / 4u;
-            if (ttid == 0 && nrec) {
-                // u16 counter halves: whoever pushes the CTA-wide record count over the mark drains
-                const uint32_t before = atomicAdd(&cta.recs_since_flush, nrec);
-                if (before + nrec >= 24000u) {
-                    atomicExch(&cta.recs_since_flush, 0u);
-                    ctl.flush_iter = k;
+            const uint32_t first = (uint32_t)((hw + C::HW - (k % C::HW)) % C::HW);
+            const unsigned long long idx_base = mk.base - line_base;   // buffer-local number of the first own line
+            const unsigned long long off_base = p.stream_offset + mk.ts;
+            if (hw == 0 && lane == 0 && nrec) {
+                // u16 counter halves: when the CTA-wide record count passes the mark, every record warp
+                // drains its slice of the table before its next tile
+                const uint32_t tot = cta.recs_since_flush + nrec;
+                if (tot >= 24000u) {
+                    cta.recs_since_flush = 0;
+                    atomicAdd(&cta.flush_epoch, 1u);
+                } else {
+                    cta.recs_since_flush = tot;
                 }
             }
             if (!overflow) {
-                if (want_index) {
-                    for (uint32_t i = ttid; i < own_count; i += C::TT) {
-                        const unsigned long long gi = idx_base + i;
-                        if (gi < p.index_cap) p.index[gi] = (uint32_t)(off_base + (uint32_t)list[f + i] - FRONT);
+                const bool nonascii = sc.nonascii != 0;
+                const uint32_t nitems = npass + (want_index ? 1u : 0u);
+                for (uint32_t item = first; item < nitems; item += C::HW) {
+                    if (item < npass) {
+                        if (nonascii)
+                            records_pass<C, false>(p, tv, lc, hist, lenh, limit, item, acc, lane);
+                        else
+                            records_pass<C, true>(p, tv, lc, hist, lenh, limit, item, acc, lane);
+                    } else {
+                        for (uint32_t i = lane; i < mk.own_count; i += 32) {
+                            const unsigned long long gi = idx_base + i;
+                            if (gi < p.index_cap) p.index[gi] = (uint32_t)(off_base + (uint32_t)tv.list[tv.f + i] - FRONT);
+                        }
                     }
-                }
-                const bool nonascii = ctl.nonascii_iter[k & 1] == k + 1;
-                for (;;) {
-                    uint32_t pass = 0;
-                    if (lane == 0) pass = atomicAdd(&ctl.pass_counter[k & 1], 1u);
-                    pass = __shfl_sync(0xffffffffu, pass, 0);
-                    if (pass >= npass) break;
-                    if (nonascii)
-                        records_pass<C, false>(p, mk, tile, list, hist, lenh, limit, pass, acc, lane);
-                    else
-                        records_pass<C, true>(p, mk, tile, list, hist, lenh, limit, pass, acc, lane);
                 }
             } else {
-                // dense-newline tile (more line ends than the list holds; never a healthy FASTQ):
-                // redo the ranking straight into the index, then walk the records one by one
-                if (want_index && warp > 0) {
-                    const uint32_t* unit_all_k = ctl.unit_all[k & 1];
-                    uint32_t cnt[C::UPL];
-#pragma unroll
-                    for (int r = 0; r < C::UPL; ++r) cnt[r] = (lane + 32 * r) < C::NUNITS ? unit_all_k[lane + 32 * r] : 0u;
-                    for (int u = warp - 1; u < C::NUNITS; u += C::SW) {
-                        const uint32_t off = (uint32_t)u * UNIT + (uint32_t)lane * 16u;
-                        uint32_t mm = nlmask16(*reinterpret_cast<const uint4*>(tile + FRONT + off));
-                        const int c = __popc(mm);
-                        int pre = 0;
-                        for (int lvl = 0;; ++lvl) {
-                            const unsigned b = __ballot_sync(0xffffffffu, c > lvl);
-                            if (!b) break;
-                            pre += __popc(b & lt_mask);
-                        }
-                        uint32_t rank = unit_prefix<C::UPL>(cnt, u, lane, 0u) + (uint32_t)pre;   // rank among own+halo
-                        while (mm) {
-                            const uint32_t bit = (uint32_t)__ffs(mm) - 1u;
-                            mm &= mm - 1u;
-                            if (rank < own_count && idx_base + rank < p.index_cap)
-                                p.index[idx_base + rank] = (uint32_t)(off_base + off + bit);
-                            ++rank;
-                        }
-                    }
-                }
-                if (warp == 0 && j0 < nown) {
-                    unsigned long long s = mk.ts + (uint32_t)list[j0] + 1u - FRONT;   // j0 < 4 <= LIST_CAP: stored
+                // dense-newline tile: one warp walks the records one by one, another ranks the index
+                if (first == 0 && tv.j0 < tv.nown) {
+                    unsigned long long s = mk.ts + (uint32_t)tv.list[tv.j0] + 1u - FRONT;   // j0 < 4 <= LIST_CAP: stored
                     const unsigned long long tend = mk.ts + mk.own_len;
                     while (s < tend && s < limit) {
                         const unsigned long long e = record_global<C>(p, s, limit, hist, lenh, lane);
@@ -705,15 +810,24 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                         s = e + 1;
                     }
                 }
+                if (want_index && first == (uint32_t)(1 % C::HW))
+                    index_dense<C>(p, tv.tile, mk.own_count, idx_base, off_base, lane);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sc.freed);
+            if (hw == 0 && lane == 0) trace_ev(p, k, 8);
+            if (lane == 0) trace_ev(p, k, 9, true);
+            const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(&cta.flush_epoch);
+            if (ep != my_epoch) {
+                my_epoch = ep;
+                flush_hist<C>(hist, p, hw * SLICE, min((hw + 1) * SLICE, C::HIST_WORDS), lane, 32);
             }
         }
-        team_bar<C::TT>(team);   // BAR2: tile k consumed, tile k+1 described
-        if (ctl.flush_iter == k) flush_hist<C>(hist, p, ttid, C::TT);
     }
 
     // ---- drain -----------------------------------------------------------------------------
     __syncthreads();
-    flush_hist<C>(hist, p, tid, 1024);
+    flush_hist<C>(hist, p, 0, C::HIST_WORDS, tid, 1024);
     {
         unsigned long long* lenh_g = p.stats + stats_len_off(p.max_len);
         for (int i = tid; i < C::PPAD + 2; i += 1024) {
@@ -736,8 +850,8 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-using Cfg5 = Cfg<5, 2, 16384, 3>;    // P <= 160
-using Cfg10 = Cfg<10, 2, 8192, 2>;   // P <= 320 (longer reads: positions >= 320 go to global atomics)
+using Cfg5 = Cfg<5, 16384, 4, 12>;    // P <= 160: 34 units over 12 scan warps (3 each), 18 record warps
+using Cfg10 = Cfg<10, 8192, 3, 9>;    // P <= 320 (longer reads: positions >= 320 go to global atomics)
 
 size_t scan_smem_bytes(int nchunk) { return nchunk <= 5 ? (size_t)Cfg5::TOTAL : (size_t)Cfg10::TOTAL; }
 uint32_t scan_tile_bytes(int nchunk) { return nchunk <= 5 ? (uint32_t)Cfg5::TILE : (uint32_t)Cfg10::TILE; }
