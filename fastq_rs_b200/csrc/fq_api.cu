@@ -20,7 +20,7 @@ using namespace fq;
 
 namespace {
 
-__global__ void fq_init_kernel(DevResult* r, unsigned int* ticket)
+__global__ void fq_init_kernel(DevResult* r)
 {
     r->first_bad = NONE64;
     r->tail_start = NONE64;
@@ -30,7 +30,7 @@ __global__ void fq_init_kernel(DevResult* r, unsigned int* ticket)
     r->n_records = 0;
     r->status = 0;
     r->finished = 0;
-    *ticket = 0;
+    r->spec_fail = 0;
 }
 
 struct Slot {  // one stage of the streaming ring
@@ -59,9 +59,9 @@ struct fqb_ctx {
     uint64_t* d_stats = nullptr;
     uint64_t* d_seqraw = nullptr;
     DevResult* d_res = nullptr;
-    unsigned int* d_ticket = nullptr;
-    uint64_t* d_status = nullptr;
-    size_t status_cap = 0;
+    RangeInfo* d_ranges = nullptr;
+    uint32_t* d_index_stage = nullptr;  // speculative launch: per-range staging of the line ends
+    size_t index_stage_cap = 0;
     unsigned long long* d_linecount = nullptr;
     DevResult* h_res = nullptr;  // pinned
     unsigned long long* h_linecount = nullptr;
@@ -174,7 +174,7 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(cudaMalloc(&ctx->d_stats, ctx->nwords * 8));
     CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
     CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
-    CKC(cudaMalloc(&ctx->d_ticket, 16));
+    CKC(cudaMalloc(&ctx->d_ranges, sizeof(RangeInfo) * ctx->grid));
     CKC(cudaMalloc(&ctx->d_linecount, 8));
     CKC(cudaMalloc(&ctx->d_carry, sizeof(DevCarry)));
     CKC(cudaHostAlloc(&ctx->h_res, sizeof(DevResult), cudaHostAllocDefault));
@@ -221,8 +221,8 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_seqraw);
     cudaFree(ctx->d_res);
-    cudaFree(ctx->d_ticket);
-    cudaFree(ctx->d_status);
+    cudaFree(ctx->d_ranges);
+    cudaFree(ctx->d_index_stage);
     cudaFree(ctx->d_linecount);
     cudaFree(ctx->d_carry);
     cudaFree(ctx->d_trace);
@@ -235,8 +235,10 @@ void fqb_destroy(fqb_ctx* ctx)
 }
 
 // Enqueue the whole parse of one shard on `st`:
-//   reset -> scan (K1+K2) -> diagnose -> [reset + scan again, restricted to records before the
-//   first bad one: each() delivers exactly those, src/lib.rs:226-237] -> finalize
+//   reset -> scan (K1+K2; every CTA range infers its line phase) -> verify -> [reset + scan with the
+//   exact range bases, only if an inference failed] -> diagnose -> [reset + scan again, restricted to
+//   records before the first bad one: each() delivers exactly those, src/lib.rs:226-237]
+//   -> index compaction -> finalize
 static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, DevCarry* carry, uint64_t* total,
                          bool timed)
 {
@@ -247,15 +249,15 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     const uint64_t tile_bytes = scan_tile_bytes(ctx->nchunk);
     const uint64_t ntiles64 = (sh->n_own + tile_bytes - 1) / tile_bytes;
     if (ntiles64 > 0xFFFFFFF0ull) return FQB_E_ARG;
-    if (ntiles64 > ctx->status_cap) {
-        if (ctx->d_status) {
+    const bool want_index = (sh->flags & FQB_F_INDEX) && sh->d_index && sh->index_cap;
+    if (want_index && sh->index_cap > ctx->index_stage_cap) {
+        if (ctx->d_index_stage) {
             CK(cudaStreamSynchronize(st));
-            CK(cudaFree(ctx->d_status));
-            ctx->d_status = nullptr;
+            CK(cudaFree(ctx->d_index_stage));
+            ctx->d_index_stage = nullptr;
         }
-        size_t cap = std::max<size_t>(ntiles64, 4096);
-        CK(cudaMalloc(&ctx->d_status, cap * 8));
-        ctx->status_cap = cap;
+        CK(cudaMalloc(&ctx->d_index_stage, sh->index_cap * 4 + 64));
+        ctx->index_stage_cap = sh->index_cap;
     }
     ScanParams p;
     memset(&p, 0, sizeof p);
@@ -269,8 +271,13 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     if ((p.flags & F_FRONT16) && (p.flags & F_LINE_START)) return FQB_E_ARG;
     p.max_len = ctx->P;
     p.ntiles = (uint32_t)ntiles64;
-    p.tile_status = reinterpret_cast<unsigned long long*>(ctx->d_status);
-    p.ticket = ctx->d_ticket;
+    p.tiles_per_cta = (uint32_t)((ntiles64 + ctx->grid - 1) / ctx->grid);
+    p.ranges = ctx->d_ranges;
+    p.index_stage = ctx->d_index_stage;
+    {
+        const uint64_t live = p.tiles_per_cta ? (ntiles64 + p.tiles_per_cta - 1) / p.tiles_per_cta : 1;
+        p.stage_share = want_index ? sh->index_cap / (live ? live : 1) : 0;
+    }
     p.index = sh->d_index;
     p.index_cap = sh->index_cap;
     p.res = ctx->d_res;
@@ -279,11 +286,10 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, ctx->d_ticket);
+    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
-    if (p.ntiles) CK(cudaMemsetAsync(ctx->d_status, 0, (size_t)p.ntiles * 8, st));
     ctx->launches += 1;
     if (p.ntiles) {
         if (timed) CK(cudaEventRecord(ctx->ev0, st));
@@ -292,13 +298,24 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             CK(cudaEventRecord(ctx->ev1, st));
             ctx->ev_valid = true;
         }
+        // exact line numbers of the CTA ranges; redo with them if a range inferred its phase wrongly
+        CK(launch_verify(p, carry, ctx->grid, st));
+        CK(launch_rerun_reset(p, 0, st));
+        ScanParams p1 = p;
+        p1.flags |= F_BASES;
+        p1.trace = nullptr;
+        CK(launch_scan(p1, ctx->nchunk, ctx->grid, st));
+        // classify the first bad record; redo restricted to the records before it (each() delivers those)
         CK(launch_diagnose(p, carry, st));
-        CK(launch_rerun_reset(p, st));
-        ScanParams p2 = p;
+        CK(launch_rerun_reset(p, 1, st));
+        ScanParams p2 = p1;
         p2.flags |= F_RERUN;
-        p2.trace = nullptr;
         CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
-        ctx->launches += 4;
+        ctx->launches += 7;
+        if (want_index) {
+            CK(launch_compact(p, carry, ctx->grid, st));
+            ctx->launches += 1;
+        }
     }
     CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), st));
     ctx->launches += 1;

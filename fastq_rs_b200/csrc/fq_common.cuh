@@ -21,8 +21,8 @@ constexpr unsigned long long NONE64 = ~0ull;
 constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0x08, F_FRONT16 = 0x10;
 constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad
 constexpr uint32_t F_CARRY = 0x200;        // internal: streaming, line_base comes from the carry block
+constexpr uint32_t F_BASES = 0x400;        // internal: ranges[b].base holds the exact line number of every CTA range
 
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
 // device-resident outcome of one parse (mirrors fqb_result, plus scratch)
 struct DevResult {
@@ -34,6 +34,16 @@ struct DevResult {
     unsigned long long n_records;
     int status;
     int finished;
+    int spec_fail;                  // a CTA range could not infer / mis-inferred its line phase: redo with exact bases
+    int pad;
+};
+
+// one contiguous range of tiles = the work of one CTA
+struct RangeInfo {
+    unsigned long long count;       // '\n' in the owned bytes of the range (phase independent)
+    unsigned long long base;        // exact stream line number at the range start (fq_verify_kernel)
+    uint32_t spec_phase;            // line number mod 4 the CTA inferred from the first records of its range
+    uint32_t flags;                 // 1 = inferred, 2 = inference failed (ambiguous or nothing to test)
 };
 
 // streaming carry block (device resident, lives across chunk launches)
@@ -55,9 +65,10 @@ struct ScanParams {
     uint32_t flags;
     uint32_t max_len;               // P
     uint32_t ntiles;
-    uint32_t pad;
-    unsigned long long* tile_status;
-    unsigned int* ticket;
+    uint32_t tiles_per_cta;         // CTA b owns the tiles [b * tiles_per_cta, (b + 1) * tiles_per_cta)
+    RangeInfo* ranges;              // [gridDim.x]
+    uint32_t* index_stage;          // speculative run: CTA b stages its line ends at index_stage + b * stage_share
+    unsigned long long stage_share;
     uint32_t* index;
     unsigned long long index_cap;
     DevResult* res;
@@ -79,7 +90,9 @@ cudaError_t scan_configure();
 int scan_blocks_per_sm(int nchunk);
 cudaError_t launch_scan(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t st);
-cudaError_t launch_rerun_reset(const ScanParams& p, cudaStream_t st);
+cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st);
+cudaError_t launch_verify(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+cudaError_t launch_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);
 cudaError_t launch_synth_fixed(uint8_t* out, unsigned long long n, unsigned long long byte_off, uint32_t L,

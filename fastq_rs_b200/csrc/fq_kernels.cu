@@ -79,18 +79,76 @@ __global__ void fq_diagnose_kernel(const ScanParams p, DevCarry* carry)
     }
 }
 
-// zero the accumulators for the second pass -- only when there is something to redo
-__global__ void fq_rerun_reset_kernel(const ScanParams p)
+// zero the accumulators before a conditional relaunch -- only when there is something to redo
+//   mode 0: before the exact-bases launch (runs when the phase inference failed): everything the
+//           speculative launch produced is void, including its error flags
+//   mode 1: before the launch restricted to the records in front of the first bad one
+__global__ void fq_rerun_reset_kernel(const ScanParams p, int mode)
 {
-    if (p.res->first_bad == NONE64) return;
+    if (mode == 0 ? p.res->spec_fail == 0 : p.res->first_bad == NONE64) return;
     const size_t n_stats = stats_words(p.max_len);
     const size_t n_seq = (size_t)p.max_len * 256;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = i0; i < n_stats; i += stride) p.stats[i] = 0;
     for (size_t i = i0; i < n_seq; i += stride) p.seqraw[i] = 0;
-    for (size_t i = i0; i < p.ntiles; i += stride) p.tile_status[i] = 0;
-    if (i0 == 0) *p.ticket = 0;
+    if (mode == 0 && i0 == 0) {
+        p.res->first_bad = NONE64;
+        p.res->tail_start = NONE64;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// verify: exact line number of every CTA range = prefix of the per-range newline counts; compare
+// with the phases the CTAs inferred.  One warp.
+// ------------------------------------------------------------------------------------------
+__global__ void fq_verify_kernel(const ScanParams p, DevCarry* carry, int nranges)
+{
+    const int lane = threadIdx.x;
+    if (carry && carry->status != 0) return;
+    const unsigned long long line_base = carry ? carry->line_base : p.line_base;
+    unsigned long long run = line_base;
+    int fail = 0;
+    for (int b0 = 0; b0 < nranges; b0 += 32) {
+        const int b = b0 + lane;
+        const bool live = b < nranges && (unsigned long long)b * p.tiles_per_cta < p.ntiles;
+        const unsigned long long c = live ? p.ranges[b].count : 0ull;
+        unsigned long long incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const unsigned long long base = run + incl - c;
+        if (live) {
+            p.ranges[b].base = base;
+            if (b > 0 && (p.ranges[b].flags != 1u || p.ranges[b].spec_phase != (uint32_t)(base & 3ull))) fail = 1;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    fail = __any_sync(0xffffffffu, fail);
+    if (lane == 0) {
+        if (fail) p.res->spec_fail = 1;   // (the CTAs may have raised it already)
+        p.res->n_lines = run - line_base;
+        p.res->line_end = run;
+    }
+}
+
+// move the staged line ends of every range to their place in the caller's index (only when the
+// speculative launch stands; the exact launch writes the index directly)
+__global__ void fq_index_compact_kernel(const ScanParams p, DevCarry* carry)
+{
+    if (p.res->spec_fail) return;
+    if (carry && carry->status != 0) return;
+    const unsigned long long line_base = carry ? carry->line_base : p.line_base;
+    const int b = blockIdx.x;
+    if ((unsigned long long)b * p.tiles_per_cta >= p.ntiles) return;
+    const RangeInfo ri = p.ranges[b];
+    const uint32_t* src = p.index_stage + (size_t)b * p.stage_share;
+    const unsigned long long dst0 = ri.base - line_base;
+    const unsigned long long stride = (unsigned long long)gridDim.y * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.y * blockDim.x + threadIdx.x; i < ri.count; i += stride)
+        if (dst0 + i < p.index_cap) p.index[dst0 + i] = src[i];
 }
 
 // fold the raw sequence-byte histogram into the six base classes (validate_dnan's alphabet,
@@ -287,9 +345,21 @@ cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_rerun_reset(const ScanParams& p, cudaStream_t st)
+cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st)
 {
-    fq_rerun_reset_kernel<<<256, 256, 0, st>>>(p);
+    fq_rerun_reset_kernel<<<256, 256, 0, st>>>(p, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+{
+    fq_verify_kernel<<<1, 32, 0, st>>>(p, carry, grid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+{
+    fq_index_compact_kernel<<<dim3(grid, 8), 256, 0, st>>>(p, carry);
     return cudaGetLastError();
 }
 

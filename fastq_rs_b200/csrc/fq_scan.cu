@@ -1,16 +1,23 @@
-// fq_scan.cu -- the fused sm_100a scan kernel (K1 delimit + K2 per-position histograms), v5.
+// fq_scan.cu -- the fused sm_100a scan kernel (K1 delimit + K2 per-position histograms), v6.
 //
-// One pass over the bytes.  Persistent grid, one 1024-thread CTA per SM, static tile schedule
-// (tile = cta + k * grid).  The 32 warps of a CTA are SPECIALISED and hand tiles to each other
-// through a ring of NSTAGE shared-memory stages guarded by mbarriers -- no CTA-wide barrier in the
-// steady state:
+// One pass over the bytes.  Persistent grid, one 1024-thread CTA per SM; CTA b owns a CONTIGUOUS
+// range of tiles, so the stream line number of a tile is the line number of the range start plus a
+// running count the CTA keeps itself -- no look-back, no coupling between CTAs while they run.
+// The line number of a range start (mod 4 it decides which lines are headers) is not known before
+// the ranges in front of it have been counted, so the first launch INFERS it: the CTA tests the four
+// possible phases against the grammar over the first records of its range ('@', '+', equal raw
+// lengths) and proceeds with the only one that holds.  fq_verify_kernel then compares every
+// inferred phase with the exact prefix of the per-range newline counts (which do not depend on the
+// phase); any mismatch or ambiguity makes the host-enqueued second launch redo the shard with the
+// exact bases (F_BASES).  Results therefore never depend on the inference.
+//
+// The 32 warps of a CTA are SPECIALISED and hand tiles to each other through a ring of NSTAGE
+// shared-memory stages guarded by mbarriers -- no CTA-wide barrier in the steady state:
 //
 //   TMA warp (1)       keeps the ring full: UBLKCP bulk copies completing on full[s]
-//   look-back warp (1) resolves the stream line number of every tile with a decoupled look-back over
-//                      the newline counts the other CTAs publish; runs concurrently with the scan
 //   scan warps (SW)    16-byte SWAR newline masks (3 ops / word + dp4a bit gather) -> per-unit counts
-//                      -> ranks -> position list of the tile (u16, shared memory); publish the tile's
-//                      newline count for the look-backs of the other CTAs
+//                      -> ranks -> position list of the tile (u16, shared memory); scan warp 0 keeps
+//                      the running line number of the range
 //   record warps (HW)  8 lanes per record: '@' / '+' / raw-length validation
 //                      (src/records.rs:201-247), then each lane walks 4-byte groups of the sequence
 //                      and quality lines and bumps hist[chunk][byte][position % 32] with one dp4a
@@ -18,8 +25,7 @@
 //                      and the (group, byte) rotation make the 32 lanes of every ATOMS hit 32 banks.
 //                      They also copy the line-end list to the global index.
 //
-//   full[s]    TMA -> scan + look-back      scanned[s]  scan warps -> look-back + record warps
-//   based[s]   look-back -> record warps    freed[s]    record warps + look-back -> TMA warp
+//   full[s]  TMA -> scan warps     scanned[s]  scan warps -> record warps     freed[s]  record warps -> TMA
 //
 // Reference behaviour reproduced: see fq_kernels.cu header.
 #include "fq_common.cuh"
@@ -31,7 +37,7 @@ template <int NCHUNK_, int TILE_, int NSTAGE_, int SCANW_>
 struct Cfg {
     static constexpr int NCHUNK = NCHUNK_, TILE = TILE_, NSTAGE = NSTAGE_;
     static constexpr int SW = SCANW_;                      // scan warps
-    static constexpr int HW = 30 - SCANW_;                 // record / histogram warps (warps 0, 1: TMA, look-back)
+    static constexpr int HW = 31 - SCANW_;                 // record / histogram warps (warp 0: TMA)
     static constexpr int PPAD = 32 * NCHUNK;               // positions with a shared-memory counter column
     static constexpr int SM_TILE = FRONT + TILE + HALO;
     static constexpr int TILE_PAD = (SM_TILE + 16 + 127) / 128 * 128;
@@ -54,7 +60,8 @@ struct Cfg {
 };
 
 struct TileMeta {
-    unsigned long long base;   // stream-global exclusive line count at the tile start (control warp)
+    unsigned long long base;   // line number at the tile start (exact, or exact mod 4 when inferred)
+    unsigned long long lrank;  // '\n' of the range before the tile
     unsigned long long ts;     // buffer-relative offset of the tile
     uint32_t front;            // 1 if the byte before the tile is (or acts as) '\n'
     uint32_t own_count;        // '\n' in the owned range
@@ -66,8 +73,7 @@ template <int NUNITS>
 struct StageCtl {
     unsigned long long full;      // mbarrier: tile bytes landed (TMA)
     unsigned long long scanned;   // mbarrier: position list + meta complete (SW arrivals)
-    unsigned long long based;     // mbarrier: meta.base known (control warp)
-    unsigned long long freed;     // mbarrier: stage may be overwritten (HW + 1 arrivals)
+    unsigned long long freed;     // mbarrier: stage may be overwritten (HW arrivals)
     TileMeta meta;
     uint32_t unit_all[NUNITS + 2];
     uint32_t unit_own[NUNITS + 2];
@@ -416,50 +422,6 @@ __device__ __forceinline__ void records_pass(const ScanParams& p, const TileView
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// decoupled look-back with a wide window: all loads of a 128-entry chunk are in flight together
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long look_back(const unsigned long long* status, uint32_t t, int lane)
-{
-    unsigned long long excl = 0;
-    long long pos = (long long)t - 1;   // nearest predecessor
-    for (;;) {
-        unsigned long long v[4];
-        bool ready;
-        for (;;) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const long long idx = pos - 32 * r - lane;
-                v[r] = idx >= 0 ? ld_volatile_u64(status + idx) : ST_INC;
-            }
-            // entries are needed up to the nearest inclusive one
-            ready = true;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const unsigned inc = __ballot_sync(0xffffffffu, (v[r] >> 62) == 2);
-                const unsigned nil = __ballot_sync(0xffffffffu, (v[r] >> 62) == 0);
-                const unsigned below = inc ? ((inc & (0u - inc)) - 1u) : 0xffffffffu;  // lanes nearer than the first inclusive
-                if (nil & below) ready = false;
-                if (inc || !ready) break;
-            }
-            if (ready) break;
-            __nanosleep(100);   // the predecessors are still scanning: leave the issue slots to the other warps
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned inc = __ballot_sync(0xffffffffu, (v[r] >> 62) == 2);
-            const unsigned long long val = v[r] & ST_VAL;
-            if (inc) {
-                const int first = __ffs(inc) - 1;
-                excl += warp_sum_u64(lane <= first ? val : 0ull);
-                return excl;
-            }
-            excl += warp_sum_u64(val);
-        }
-        pos -= 128;
-    }
-}
-
 // warp-exclusive prefix of small per-lane counts (most are 0, a few 1 or 2): ballot levels
 __device__ __forceinline__ uint32_t small_prefix(int c, uint32_t lt_mask)
 {
@@ -481,8 +443,9 @@ __device__ __forceinline__ uint32_t small_prefix(int c, uint32_t lt_mask)
 // line ends of the owned range of a dense-newline tile (more than the list holds; never a healthy
 // FASTQ), ranked straight into the index by one warp
 template <class C>
-__device__ __noinline__ void index_dense(const ScanParams& p, const uint8_t* tile, uint32_t own_count,
-                                         unsigned long long idx_base, unsigned long long off_base, int lane)
+__device__ __noinline__ void index_dense(uint32_t* idx_out, unsigned long long idx_cap, const uint8_t* tile,
+                                         uint32_t own_count, unsigned long long idx_base,
+                                         unsigned long long off_base, int lane)
 {
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t run = 0;
@@ -494,11 +457,42 @@ __device__ __noinline__ void index_dense(const ScanParams& p, const uint8_t* til
         while (mm) {
             const uint32_t bit = (uint32_t)__ffs(mm) - 1u;
             mm &= mm - 1u;
-            if (rank < own_count && idx_base + rank < p.index_cap)
-                p.index[idx_base + rank] = (uint32_t)(off_base + off + bit);
+            if (rank < own_count && idx_base + rank < idx_cap)
+                idx_out[idx_base + rank] = (uint32_t)(off_base + off + bit);
             ++rank;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase inference at the start of a CTA range (one warp): which list entry j0 in 0..3 is followed by
+// a record start?  lane = 8 * candidate + r tests record r of the candidate: '@' after entry j,
+// '+' after entry j + 2, equal raw lengths.  Accepted only if exactly one candidate passes all the
+// records it could test (at least two).  Returns j0, or 4 when the range start is ambiguous.
+// ------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ uint32_t infer_j0(const uint8_t* tile, const uint16_t* list, uint32_t nstored, int lane)
+{
+    const uint32_t cand = (uint32_t)lane >> 3, r = (uint32_t)lane & 7u;
+    const uint32_t j = cand + 4u * r;
+    const bool testable = j + 4u < nstored;
+    bool good = true;
+    if (testable) {
+        const uint32_t s = (uint32_t)list[j] + 1u, h = list[j + 1], q = list[j + 2], pp = list[j + 3], e = list[j + 4];
+        good = tile[s] == '@' && tile[q + 1] == '+' && (e - pp) == (q - h);
+    }
+    const unsigned tested = __ballot_sync(0xffffffffu, testable);
+    const unsigned bad = __ballot_sync(0xffffffffu, testable && !good);
+    uint32_t pass = 0, npass = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c) {
+        const unsigned m = 0xFFu << (8 * c);
+        if (__popc(tested & m) >= 2 && !(bad & m)) {
+            pass = c;
+            ++npass;
+        }
+    }
+    return npass == 1 ? pass : 4u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -515,14 +509,18 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;                    // 0 = TMA, 1 = look-back, 2..SW+1 = scan, rest = records
+    const int warp = tid >> 5;                    // 0 = TMA, 1..SW = scan, rest = records
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint8_t* stage_mem = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4;
 
+    // launch 1 infers the range phases; launch 2 (F_BASES) runs only when the inference failed;
+    // launch 3 (F_BASES | F_RERUN) only when a bad record was found, restricted to the records before it
     unsigned long long limit = NONE64;
     if (p.flags & F_RERUN) {
-        limit = p.res->first_bad;                 // written by the first pass, stable during this launch
+        limit = p.res->first_bad;                 // written by the earlier launches, stable during this one
         if (limit == NONE64) return;
+    } else if ((p.flags & F_BASES) && !p.res->spec_fail) {
+        return;
     }
     if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
     const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
@@ -532,8 +530,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
         for (int s = 0; s < C::NSTAGE; ++s) {
             mbar_init(&stage_ctl[s].full, 1);
             mbar_init(&stage_ctl[s].scanned, C::SW);
-            mbar_init(&stage_ctl[s].based, 1);
-            mbar_init(&stage_ctl[s].freed, C::HW + 1);
+            mbar_init(&stage_ctl[s].freed, C::HW);
             stage_ctl[s].nonascii = 0;
         }
         fence_mbar_init();
@@ -542,17 +539,21 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    // static schedule: CTA b of G handles tiles b, b + G, ...
-    const uint32_t G = gridDim.x;
+    // static schedule: CTA b handles the tiles [b * tiles_per_cta, (b + 1) * tiles_per_cta)
     uint32_t ntiles_eff = p.ntiles;
     if (limit != NONE64) {
         const unsigned long long lt = limit / C::TILE + 1;   // tiles that start below the limit
         if (lt < ntiles_eff) ntiles_eff = (uint32_t)lt;
     }
-    const int K = blockIdx.x < ntiles_eff ? (int)((ntiles_eff - blockIdx.x + G - 1) / G) : 0;
-    const bool want_index = (p.flags & F_INDEX) && !(p.flags & F_RERUN) && p.index != nullptr;
+    const unsigned long long tile0 = (unsigned long long)blockIdx.x * p.tiles_per_cta;
+    const int K = tile0 < ntiles_eff ? (int)min((unsigned long long)p.tiles_per_cta, ntiles_eff - tile0) : 0;
+    // the range of CTA 0 starts at the shard start, whose line number the caller gave; the others
+    // infer theirs unless the exact bases are there
+    const bool infer = blockIdx.x != 0 && !(p.flags & F_BASES);
+    const bool staged_index = !(p.flags & F_BASES);          // ranks relative to the range -> index_stage
+    const bool want_index = (p.flags & F_INDEX) && !(p.flags & F_RERUN) && p.index != nullptr && p.index_cap != 0;
 
-    auto tile_no = [&](int k) -> uint32_t { return blockIdx.x + (uint32_t)k * G; };
+    auto tile_no = [&](int k) -> uint32_t { return (uint32_t)tile0 + (uint32_t)k; };
     auto tile_buf = [&](int k) -> uint8_t* { return stage_mem + (k % C::NSTAGE) * (C::TILE_PAD + C::LIST_BYTES); };
     auto tile_list = [&](int k) -> uint16_t* { return reinterpret_cast<uint16_t*>(tile_buf(k) + C::TILE_PAD); };
 
@@ -578,40 +579,15 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // =====================================================================================
-        // look-back warp: stream line number of every tile, concurrently with its scan
-        // =====================================================================================
-        for (int k = 0; k < K; ++k) {
-            StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
-            const uint32_t par = (uint32_t)(k / C::NSTAGE) & 1u;
-            mbar_wait(&sc.full, par);             // the stage now belongs to tile k
-            const uint32_t t = tile_no(k);
-            if (lane == 0) trace_ev(p, k, 4);
-            const unsigned long long excl = t == 0 ? line_base : look_back(p.tile_status, t, lane);
-            if (lane == 0) sc.meta.base = excl;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sc.based);
-            if (lane == 0) trace_ev(p, k, 5);
-            mbar_wait(&sc.scanned, par);
-            if (lane == 0) {
-                const uint32_t own_count = sc.meta.own_count;
-                if (t) st_volatile_u64(p.tile_status + t, ST_INC | (excl + own_count));
-                if (t == p.ntiles - 1 && !(p.flags & F_RERUN)) {
-                    p.res->n_lines = excl + own_count - line_base;
-                    p.res->line_end = excl + own_count;
-                }
-                mbar_arrive(&sc.freed);
-                trace_ev(p, k, 6);
-            }
-            __syncwarp();
-        }
-    } else if (warp < 2 + C::SW) {
+    } else if (warp <= C::SW) {
         // =====================================================================================
         // scan warps: newline masks -> unit counts -> ranks -> position list
         // warp sw owns the units [sw * ITERS, (sw + 1) * ITERS) of every tile
         // =====================================================================================
-        const int sw = warp - 2;
+        const int sw = warp - 1;
+        unsigned long long lbase = blockIdx.x == 0 ? line_base : ((p.flags & F_BASES) ? p.ranges[blockIdx.x].base : 0ull);
+        unsigned long long lrank = 0;
+        uint32_t spec_phase = 0, spec_flags = 0;
         const int sthreads = C::SW * 32;
         const int stid = sw * 32 + lane;
         const int u0 = sw * C::ITERS;
@@ -676,6 +652,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
             uint32_t cnt[C::UPL];
 #pragma unroll
             for (int r = 0; r < C::UPL; ++r) cnt[r] = (lane + 32 * r) < C::NUNITS ? sc.unit_all[lane + 32 * r] : 0u;
+            uint32_t own_count_t = 0;
             if (sw == 0) {
                 uint32_t a = 0, o = 0;
 #pragma unroll
@@ -684,18 +661,16 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     o += (lane + 32 * r) < C::NUNITS ? sc.unit_own[lane + 32 * r] : 0u;
                 }
                 const uint32_t total = __reduce_add_sync(0xffffffffu, a);
-                const uint32_t own_count = __reduce_add_sync(0xffffffffu, o);
+                own_count_t = __reduce_add_sync(0xffffffffu, o);
                 if (lane == 0) {
+                    sc.meta.base = lbase;
+                    sc.meta.lrank = lrank;
                     sc.meta.ts = ts;
                     sc.meta.front = f;
-                    sc.meta.own_count = own_count;
+                    sc.meta.own_count = own_count_t;
                     sc.meta.total_count = total;
                     sc.meta.own_len = own_len;
                     if (f) list[0] = FRONT - 1;
-                    if (tn == 0)
-                        st_volatile_u64(p.tile_status, ST_INC | (line_base + own_count));
-                    else
-                        st_volatile_u64(p.tile_status + tn, ST_AGG | own_count);
                 }
             }
             // ---- pass 2: rank every newline, fill the position list --------------------------------
@@ -725,17 +700,47 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     ubase += call[it];
                 }
             }
+            if (infer && k == 0) {
+                // the first tile of the range: its complete list decides the phase of the whole range
+                __syncwarp();
+                named_bar(1, sthreads);
+                if (sw == 0) {
+                    const uint32_t nstored = min(f + sc.meta.total_count, (uint32_t)C::LIST_CAP);
+                    const uint32_t j0 = infer_j0<C>(tile, list, nstored, lane);
+                    spec_flags = j0 < 4u ? 1u : 2u;
+                    // entry j ends line base - f + j; a record starts after every line = 3 (mod 4)
+                    spec_phase = (3u + f - (j0 & 3u)) & 3u;
+                    lbase = spec_phase;
+                    if (lane == 0) {
+                        sc.meta.base = lbase;
+                        if (j0 >= 4u) atomicExch(&p.res->spec_fail, 1);
+                    }
+                }
+            }
+            if (sw == 0) {
+                lbase += own_count_t;
+                lrank += own_count_t;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sc.scanned);
             if (stid == 0) trace_ev(p, k, 3);
             if (lane == 0) trace_ev(p, k, 10, true);
+        }
+        if (sw == 0 && lane == 0 && !(p.flags & F_RERUN)) {
+            // what fq_verify_kernel needs: the newline count of the range and the inferred phase
+            RangeInfo& ri = p.ranges[blockIdx.x];
+            ri.count = lrank;
+            if (!(p.flags & F_BASES)) {
+                ri.spec_phase = spec_phase;
+                ri.flags = spec_flags;
+            }
         }
     } else {
         // =====================================================================================
         // record warps: validation + per-position histograms + index copy; the items of a tile
         // (record passes, then one index item) are dealt round-robin, rotated from tile to tile
         // =====================================================================================
-        const int hw = warp - 2 - C::SW;
+        const int hw = warp - 1 - C::SW;
         uint32_t my_epoch = 0;
         constexpr int SLICE = (C::HIST_WORDS + C::HW - 1) / C::HW;
         LaneConst lc;
@@ -753,7 +758,6 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
             StageCtl<C::NUNITS>& sc = stage_ctl[k % C::NSTAGE];
             const uint32_t par = (uint32_t)(k / C::NSTAGE) & 1u;
             mbar_wait(&sc.scanned, par);
-            mbar_wait(&sc.based, par);
             if (hw == 0 && lane == 0) trace_ev(p, k, 7);
             const TileMeta mk = sc.meta;
             TileView tv;
@@ -770,7 +774,11 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
             const uint32_t nrec = tv.nown > tv.j0 ? (tv.nown - tv.j0 + 3u) / 4u : 0u;
             const uint32_t npass = (nrec + 3u) / 4u;
             const uint32_t first = (uint32_t)((hw + C::HW - (k % C::HW)) % C::HW);
-            const unsigned long long idx_base = mk.base - line_base;   // buffer-local number of the first own line
+            // where the line ends of this tile go: ranks relative to the range into the staging area of
+            // this CTA, or (exact bases) straight into the caller's index
+            uint32_t* const idx_out = staged_index ? p.index_stage + (size_t)blockIdx.x * p.stage_share : p.index;
+            const unsigned long long idx_cap = staged_index ? p.stage_share : p.index_cap;
+            const unsigned long long idx_base = staged_index ? mk.lrank : mk.base - line_base;
             const unsigned long long off_base = p.stream_offset + mk.ts;
             if (hw == 0 && lane == 0 && nrec) {
                 // u16 counter halves: when the CTA-wide record count passes the mark, every record warp
@@ -795,8 +803,10 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     } else {
                         for (uint32_t i = lane; i < mk.own_count; i += 32) {
                             const unsigned long long gi = idx_base + i;
-                            if (gi < p.index_cap) p.index[gi] = (uint32_t)(off_base + (uint32_t)tv.list[tv.f + i] - FRONT);
+                            if (gi < idx_cap) idx_out[gi] = (uint32_t)(off_base + (uint32_t)tv.list[tv.f + i] - FRONT);
                         }
+                        // a staging share too small for this range: the exact second launch writes the index
+                        if (staged_index && lane == 0 && idx_base + mk.own_count > idx_cap) atomicExch(&p.res->spec_fail, 1);
                     }
                 }
             } else {
@@ -811,7 +821,10 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     }
                 }
                 if (want_index && first == (uint32_t)(1 % C::HW))
-                    index_dense<C>(p, tv.tile, mk.own_count, idx_base, off_base, lane);
+                {
+                    index_dense<C>(idx_out, idx_cap, tv.tile, mk.own_count, idx_base, off_base, lane);
+                    if (staged_index && lane == 0 && idx_base + mk.own_count > idx_cap) atomicExch(&p.res->spec_fail, 1);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sc.freed);

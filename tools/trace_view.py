@@ -19,8 +19,7 @@ v = a[:, ks, :]
 ok = (v[:, :, 0] > 0) & (v[:, :, 9] > 0)
 def d(x, y):
     return float(np.mean((v[:, :, x] - v[:, :, y])[ok]))
-print("mean cycles: issue->full %.0f | full->pass1 %.0f | pass1->scanned(max) %.0f | scanned->lb_start %.0f | lb_start->based %.0f | "
-      "based->rec_start %.0f | rec_start->rec_free(max) %.0f | rec_free(max)->next issue(k+NS) ..." %
-      (d(1, 0), d(2, 1), d(10, 2), d(4, 10), d(5, 4), d(7, 5), d(9, 7)))
+print("mean cycles: issue->full %.0f | full->pass1 %.0f | pass1->scanned(max) %.0f | scanned(max)->rec_start %.0f | "
+      "rec_start->rec_free(max) %.0f | issue->rec_free(max) %.0f" % (d(1, 0), d(2, 1), d(10, 2), d(7, 10), d(9, 7), d(9, 0)))
 per_tile = np.diff(a[:, k0:k0 + 400, 0], axis=1)
 print("mean cycles between consecutive issues: %.0f" % float(np.mean(per_tile[per_tile > 0])))
