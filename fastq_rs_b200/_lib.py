@@ -53,7 +53,7 @@ class Result(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("fq_scan.cu", "fq_kernels.cu", "fq_api.cu", "fq_common.cuh", "fq_device.cuh")]
+    srcs = [os.path.join(src_dir, f) for f in ("fq_scan.cu", "fq_stream.cu", "fq_kernels.cu", "fq_api.cu", "fq_common.cuh", "fq_device.cuh", "fq_hist.cuh")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "fastq_b200.h"))
     stale = (not os.path.exists(SO_PATH)) or any(
         os.path.getmtime(p) > os.path.getmtime(SO_PATH) for p in srcs if os.path.exists(p))

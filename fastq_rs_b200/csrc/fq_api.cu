@@ -20,7 +20,7 @@ using namespace fq;
 
 namespace {
 
-__global__ void fq_init_kernel(DevResult* r)
+__global__ void fq_init_kernel(DevResult* r, int spec_fail)
 {
     r->first_bad = NONE64;
     r->tail_start = NONE64;
@@ -30,7 +30,7 @@ __global__ void fq_init_kernel(DevResult* r)
     r->n_records = 0;
     r->status = 0;
     r->finished = 0;
-    r->spec_fail = 0;
+    r->spec_fail = spec_fail;   // 1: no speculative launch, go straight to the exact path
 }
 
 struct Slot {  // one stage of the streaming ring
@@ -273,6 +273,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.ntiles = (uint32_t)ntiles64;
     p.tiles_per_cta = (uint32_t)((ntiles64 + ctx->grid - 1) / ctx->grid);
     p.ranges = ctx->d_ranges;
+    p.nranges = (uint32_t)ctx->grid;
     p.index_stage = ctx->d_index_stage;
     {
         const uint64_t live = p.tiles_per_cta ? (ntiles64 + p.tiles_per_cta - 1) / p.tiles_per_cta : 1;
@@ -286,36 +287,30 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res);
+    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, 1);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
     ctx->launches += 1;
     if (p.ntiles) {
         if (timed) CK(cudaEventRecord(ctx->ev0, st));
+        // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
+        // of the CTA ranges -> exact line numbers -> exact kernel
+        CK(launch_rerun_reset(p, 0, st));
+        CK(launch_range_count(p, carry, ctx->grid, (unsigned long long)p.tiles_per_cta * tile_bytes, st));
         CK(launch_scan(p, ctx->nchunk, ctx->grid, st));
         if (timed) {
             CK(cudaEventRecord(ctx->ev1, st));
             ctx->ev_valid = true;
         }
-        // exact line numbers of the CTA ranges; redo with them if a range inferred its phase wrongly
-        CK(launch_verify(p, carry, ctx->grid, st));
-        CK(launch_rerun_reset(p, 0, st));
-        ScanParams p1 = p;
-        p1.flags |= F_BASES;
-        p1.trace = nullptr;
-        CK(launch_scan(p1, ctx->nchunk, ctx->grid, st));
         // classify the first bad record; redo restricted to the records before it (each() delivers those)
         CK(launch_diagnose(p, carry, st));
         CK(launch_rerun_reset(p, 1, st));
-        ScanParams p2 = p1;
+        ScanParams p2 = p;
         p2.flags |= F_RERUN;
+        p2.trace = nullptr;
         CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
         ctx->launches += 7;
-        if (want_index) {
-            CK(launch_compact(p, carry, ctx->grid, st));
-            ctx->launches += 1;
-        }
     }
     CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), st));
     ctx->launches += 1;

@@ -21,7 +21,6 @@ constexpr unsigned long long NONE64 = ~0ull;
 constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0x08, F_FRONT16 = 0x10;
 constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad
 constexpr uint32_t F_CARRY = 0x200;        // internal: streaming, line_base comes from the carry block
-constexpr uint32_t F_BASES = 0x400;        // internal: ranges[b].base holds the exact line number of every CTA range
 
 
 // device-resident outcome of one parse (mirrors fqb_result, plus scratch)
@@ -66,7 +65,9 @@ struct ScanParams {
     uint32_t max_len;               // P
     uint32_t ntiles;
     uint32_t tiles_per_cta;         // CTA b owns the tiles [b * tiles_per_cta, (b + 1) * tiles_per_cta)
-    RangeInfo* ranges;              // [gridDim.x]
+    RangeInfo* ranges;              // [nranges] CTA ranges of the exact kernel
+    uint32_t nranges;
+    uint32_t pad;
     uint32_t* index_stage;          // speculative run: CTA b stages its line ends at index_stage + b * stage_share
     unsigned long long stage_share;
     uint32_t* index;
@@ -91,7 +92,8 @@ int scan_blocks_per_sm(int nchunk);
 cudaError_t launch_scan(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st);
-cudaError_t launch_verify(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges, unsigned long long range_bytes,
+                               cudaStream_t st);
 cudaError_t launch_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);

@@ -80,7 +80,7 @@ __global__ void fq_diagnose_kernel(const ScanParams p, DevCarry* carry)
 }
 
 // zero the accumulators before a conditional relaunch -- only when there is something to redo
-//   mode 0: before the exact-bases launch (runs when the phase inference failed): everything the
+//   mode 0: before the exact path (runs when the speculative kernel did not deliver): everything the
 //           speculative launch produced is void, including its error flags
 //   mode 1: before the launch restricted to the records in front of the first bad one
 __global__ void fq_rerun_reset_kernel(const ScanParams p, int mode)
@@ -92,43 +92,62 @@ __global__ void fq_rerun_reset_kernel(const ScanParams p, int mode)
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = i0; i < n_stats; i += stride) p.stats[i] = 0;
     for (size_t i = i0; i < n_seq; i += stride) p.seqraw[i] = 0;
-    if (mode == 0 && i0 == 0) {
-        p.res->first_bad = NONE64;
-        p.res->tail_start = NONE64;
+    if (mode == 0) {
+        for (size_t i = i0; i < p.nranges; i += stride) p.ranges[i].count = 0;
+        if (i0 == 0) {
+            p.res->first_bad = NONE64;
+            p.res->tail_start = NONE64;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// verify: exact line number of every CTA range = prefix of the per-range newline counts; compare
-// with the phases the CTAs inferred.  One warp.
+// exact path, step 1: '\n' count of every CTA range of the exact kernel (grid = ranges x 8 pieces)
 // ------------------------------------------------------------------------------------------
-__global__ void fq_verify_kernel(const ScanParams p, DevCarry* carry, int nranges)
+__global__ void __launch_bounds__(256) fq_range_count_kernel(const ScanParams p, const DevCarry* carry,
+                                                             unsigned long long range_bytes)
+{
+    if (!p.res->spec_fail) return;
+    if (carry && carry->status != 0) return;
+    const unsigned long long r0 = (unsigned long long)blockIdx.x * range_bytes;
+    if (r0 >= p.n_own) return;
+    const unsigned long long r1 = min(p.n_own, r0 + range_bytes);
+    // 16-byte pieces of the range, dealt to the 8 blocks of the range
+    const unsigned long long n16 = (r1 - r0) / 16;
+    const uint4* v = reinterpret_cast<const uint4*>(p.data + r0);   // range_bytes is a multiple of 16
+    unsigned long long cnt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.y * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.y * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 a = __ldg(v + i);
+        const uint32_t s = (nlbits(a.x) >> 7) + (nlbits(a.y) >> 7) + (nlbits(a.z) >> 7) + (nlbits(a.w) >> 7);
+        cnt += (s * 0x01010101u) >> 24;   // per-byte sums <= 4: no carries
+    }
+    if (blockIdx.y == 0 && threadIdx.x < ((r1 - r0) & 15)) cnt += p.data[r0 + n16 * 16 + threadIdx.x] == '\n';
+    cnt = warp_sum_u64(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&p.ranges[blockIdx.x].count, cnt);
+}
+
+// exact path, step 2: line number of every range start = prefix of the counts.  One warp.
+__global__ void fq_range_prefix_kernel(const ScanParams p, const DevCarry* carry, int nranges)
 {
     const int lane = threadIdx.x;
+    if (!p.res->spec_fail) return;
     if (carry && carry->status != 0) return;
     const unsigned long long line_base = carry ? carry->line_base : p.line_base;
     unsigned long long run = line_base;
-    int fail = 0;
     for (int b0 = 0; b0 < nranges; b0 += 32) {
         const int b = b0 + lane;
-        const bool live = b < nranges && (unsigned long long)b * p.tiles_per_cta < p.ntiles;
-        const unsigned long long c = live ? p.ranges[b].count : 0ull;
+        const unsigned long long c = b < nranges ? p.ranges[b].count : 0ull;
         unsigned long long incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        const unsigned long long base = run + incl - c;
-        if (live) {
-            p.ranges[b].base = base;
-            if (b > 0 && (p.ranges[b].flags != 1u || p.ranges[b].spec_phase != (uint32_t)(base & 3ull))) fail = 1;
-        }
+        if (b < nranges) p.ranges[b].base = run + incl - c;
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    fail = __any_sync(0xffffffffu, fail);
     if (lane == 0) {
-        if (fail) p.res->spec_fail = 1;   // (the CTAs may have raised it already)
         p.res->n_lines = run - line_base;
         p.res->line_end = run;
     }
@@ -351,9 +370,12 @@ cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_verify(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges, unsigned long long range_bytes,
+                               cudaStream_t st)
 {
-    fq_verify_kernel<<<1, 32, 0, st>>>(p, carry, grid);
+    fq_range_count_kernel<<<dim3(nranges, 8), 256, 0, st>>>(p, carry, range_bytes);
+    if (cudaGetLastError() != cudaSuccess) return cudaGetLastError();
+    fq_range_prefix_kernel<<<1, 32, 0, st>>>(p, carry, nranges);
     return cudaGetLastError();
 }
 

@@ -1,35 +1,30 @@
-// fq_scan.cu -- the fused sm_100a scan kernel (K1 delimit + K2 per-position histograms), v6.
+// fq_scan.cu -- the EXACT sm_100a scan kernel (K1 delimit + K2 per-position histograms).
 //
-// One pass over the bytes.  Persistent grid, one 1024-thread CTA per SM; CTA b owns a CONTIGUOUS
-// range of tiles, so the stream line number of a tile is the line number of the range start plus a
-// running count the CTA keeps itself -- no look-back, no coupling between CTAs while they run.
-// The line number of a range start (mod 4 it decides which lines are headers) is not known before
-// the ranges in front of it have been counted, so the first launch INFERS it: the CTA tests the four
-// possible phases against the grammar over the first records of its range ('@', '+', equal raw
-// lengths) and proceeds with the only one that holds.  fq_verify_kernel then compares every
-// inferred phase with the exact prefix of the per-range newline counts (which do not depend on the
-// phase); any mismatch or ambiguity makes the host-enqueued second launch redo the shard with the
-// exact bases (F_BASES).  Results therefore never depend on the inference.
+// This is the kernel that needs no assumption about the input: it is given the exact stream line
+// number of every CTA range (fq_range_count_kernel + fq_range_prefix_kernel count the newlines of
+// the ranges first) and therefore knows which lines are headers whatever the bytes look like.  It
+// runs (a) when the speculative warp-autonomous kernel (fq_stream.cu) reported that it could not
+// stand by its result -- malformed input, records longer than its window, ambiguous range starts --,
+// (b) for read lengths its shared-memory layout does not cover, and (c) as the relaunch restricted
+// to the records in front of the first bad one (each() delivers exactly those).
 //
-// The 32 warps of a CTA are SPECIALISED and hand tiles to each other through a ring of NSTAGE
-// shared-memory stages guarded by mbarriers -- no CTA-wide barrier in the steady state:
+// Persistent grid, one 1024-thread CTA per SM; CTA b owns a CONTIGUOUS range of tiles, so the line
+// number of a tile is the line number of the range start plus a running count.  The 32 warps of a
+// CTA are SPECIALISED and hand tiles to each other through a ring of NSTAGE shared-memory stages
+// guarded by mbarriers -- no CTA-wide barrier in the steady state:
 //
 //   TMA warp (1)       keeps the ring full: UBLKCP bulk copies completing on full[s]
 //   scan warps (SW)    16-byte SWAR newline masks (3 ops / word + dp4a bit gather) -> per-unit counts
 //                      -> ranks -> position list of the tile (u16, shared memory); scan warp 0 keeps
 //                      the running line number of the range
 //   record warps (HW)  8 lanes per record: '@' / '+' / raw-length validation
-//                      (src/records.rs:201-247), then each lane walks 4-byte groups of the sequence
-//                      and quality lines and bumps hist[chunk][byte][position % 32] with one dp4a
-//                      (address = lane base + byte * 128) and one ATOMS per byte; bank = position % 32
-//                      and the (group, byte) rotation make the 32 lanes of every ATOMS hit 32 banks.
-//                      They also copy the line-end list to the global index.
+//                      (src/records.rs:201-247), then the per-position histogram rounds of
+//                      fq_hist.cuh; they also copy the line-end list to the global index.
 //
 //   full[s]  TMA -> scan warps     scanned[s]  scan warps -> record warps     freed[s]  record warps -> TMA
 //
 // Reference behaviour reproduced: see fq_kernels.cu header.
-#include "fq_common.cuh"
-#include "fq_device.cuh"
+#include "fq_hist.cuh"
 
 namespace fq {
 
@@ -60,8 +55,7 @@ struct Cfg {
 };
 
 struct TileMeta {
-    unsigned long long base;   // line number at the tile start (exact, or exact mod 4 when inferred)
-    unsigned long long lrank;  // '\n' of the range before the tile
+    unsigned long long base;   // stream line number at the tile start
     unsigned long long ts;     // buffer-relative offset of the tile
     uint32_t front;            // 1 if the byte before the tile is (or acts as) '\n'
     uint32_t own_count;        // '\n' in the owned range
@@ -85,197 +79,6 @@ struct CtaCtl {
     uint32_t flush_epoch;
 };
 
-__device__ __forceinline__ void named_bar(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int OFF>
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ void red_add(uint32_t addr, uint32_t v)
-{
-    asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v));
-}
-__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-// debug timeline: one clock64 stamp per (tile, event); no-op unless the host set p.trace (FQB_TRACE)
-__device__ __forceinline__ void trace_ev(const ScanParams& p, int k, int ev, bool use_max = false)
-{
-    if (p.trace && k < TRACE_K) {
-        unsigned long long* slot = p.trace + ((size_t)blockIdx.x * TRACE_K + k) * 16 + ev;
-        if (use_max)
-            atomicMax(slot, (unsigned long long)clock64());
-        else
-            *slot = (unsigned long long)clock64();
-    }
-}
-
-// word index of hist[chunk][byte][position % 32]
-template <class C>
-__device__ __forceinline__ uint32_t hist_word(uint32_t byte, uint32_t pos)
-{
-    return (pos >> 5) * (uint32_t)C::CHUNK_WORDS + byte * 32u + (pos & 31u);
-}
-
-// newline mask of a 16-byte piece, shifted left by 7: bit 7 + i = byte i is '\n'
-// (the four 0x80 flags of each word are gathered by dp4a with weights 1,2,4,8 / 16,32,64,128)
-__device__ __forceinline__ uint32_t nlmask16s7(const uint4& v)
-{
-    const uint32_t m0 = nlbits(v.x), m1 = nlbits(v.y), m2 = nlbits(v.z), m3 = nlbits(v.w);
-    const uint32_t lo = dp4a_u(m1, 0x80402010u, dp4a_u(m0, 0x08040201u, 0u));
-    const uint32_t hi = dp4a_u(m3, 0x80402010u, dp4a_u(m2, 0x08040201u, 0u));
-    return lo + (hi << 8);
-}
-
-// ------------------------------------------------------------------------------------------
-// lock-free drain of the u16-pair counters: atomicExch leaves concurrent increments of the other
-// warps intact, so a slice may be flushed whenever the CTA-wide record counter says a half could
-// approach 65535
-// ------------------------------------------------------------------------------------------
-template <class C>
-__device__ void flush_hist(uint32_t* hist, const ScanParams& p, int first, int last, int tid, int nthreads)
-{
-    const uint32_t P = p.max_len;
-    unsigned long long* qual = p.stats + stats_qual_off(P);
-    for (int i = first + tid; i < last; i += nthreads) {
-        if (hist[i] == 0) continue;
-        const uint32_t v = atomicExch(hist + i, 0u);
-        const uint32_t chunk = (uint32_t)i / C::CHUNK_WORDS, r = (uint32_t)i % C::CHUNK_WORDS;
-        const uint32_t b = r >> 5, pos = chunk * 32u + (r & 31u);
-        const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-        if (pos < P) {
-            if (lo) atomicAdd(p.seqraw + (size_t)pos * 256 + b, (unsigned long long)lo);
-            if (hi) atomicAdd(qual + (size_t)pos * 256 + b, (unsigned long long)hi);
-        }
-    }
-}
-
-template <class C>
-__device__ __forceinline__ void account_record(Acc& acc, uint32_t* lenh, const ScanParams& p, uint32_t Ls, uint32_t Lq)
-{
-    const uint32_t P = p.max_len;
-    acc.n_bases += Ls;
-    if (Ls > P) acc.clip_seq += Ls - P;
-    if (Lq > P) acc.clip_qual += Lq - P;
-    const uint32_t lb = Ls <= P ? Ls : P + 1;
-    if (lb < (uint32_t)C::PPAD + 2u)
-        atomicAdd(lenh + lb, 1u);
-    else
-        atomicAdd(p.stats + stats_len_off(P) + lb, 1ull);
-}
-
-// ------------------------------------------------------------------------------------------
-// slow path: one warp walks a record in global memory (longer than the halo, or inside a tile
-// with more newlines than LIST_CAP).  Returns the offset of its final '\n', or NONE64 when the
-// record was flagged (bad / incomplete) or lies beyond `limit`.
-// ------------------------------------------------------------------------------------------
-template <class C>
-__device__ __noinline__ unsigned long long record_global(const ScanParams& p, unsigned long long s,
-                                                         unsigned long long limit, uint32_t* hist, uint32_t* lenh,
-                                                         int lane)
-{
-    if (s >= limit) return NONE64;
-    const uint8_t* __restrict__ d = p.data;
-    const unsigned long long navail = p.n_avail;
-    unsigned long long win_end = s + MAXREC;
-    const bool window_full = win_end <= navail;
-    if (win_end > navail) win_end = navail;
-    unsigned long long nl[4] = {0, 0, 0, 0};
-    int found = 0;
-    for (unsigned long long q = s; q < win_end && found < 4; q += 32) {
-        const unsigned long long a = q + lane;
-        const bool isnl = a < win_end && d[a] == '\n';
-        unsigned m = __ballot_sync(0xffffffffu, isnl);
-        while (m && found < 4) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            nl[found++] = q + b;
-        }
-    }
-    bool bad = false, tail = false;
-    if (found < 4) {
-        // incomplete inside the window: too long if the window was full; otherwise the data ended --
-        // an error at EOF, a tail to carry over when more bytes will follow (src/lib.rs:276-293)
-        if (window_full || (p.flags & F_EOF))
-            bad = true;
-        else
-            tail = true;
-    } else {
-        bad = d[s] != '@' || d[nl[1] + 1] != '+' || (nl[3] - nl[2]) != (nl[1] - nl[0]);
-    }
-    if (bad || tail) {
-        if (lane == 0) {
-            if (bad)
-                atomicMin(&p.res->first_bad, s);
-            else
-                atomicMin(&p.res->tail_start, s);
-        }
-        return NONE64;
-    }
-    if (lane == 0) atomicAdd(p.stats + 0, 1ull);   // rare path: straight to the global counters
-    if (p.flags & F_HIST) {
-        const uint32_t P = p.max_len;
-        const uint32_t Pm = P < (uint32_t)C::PPAD ? P : (uint32_t)C::PPAD;
-        const uint32_t Lr = (uint32_t)(nl[1] - nl[0] - 1);
-        const uint32_t Ls = Lr - ((Lr > 0 && d[nl[1] - 1] == '\r') ? 1u : 0u);
-        const uint32_t Lq = Lr - ((Lr > 0 && d[nl[3] - 1] == '\r') ? 1u : 0u);
-        const uint8_t* sq = d + nl[0] + 1;
-        const uint8_t* ql = d + nl[2] + 1;
-        unsigned long long* qualg = p.stats + stats_qual_off(P);
-        const uint32_t ns = Ls < P ? Ls : P, nq = Lq < P ? Lq : P;
-        for (uint32_t c = lane; c < ns; c += 32) {
-            const uint32_t b = sq[c];
-            if (c < Pm && b < (uint32_t)HIST_ROWS)
-                atomicAdd(hist + hist_word<C>(b, c), 1u);
-            else
-                atomicAdd(p.seqraw + (size_t)c * 256 + b, 1ull);
-        }
-        for (uint32_t c = lane; c < nq; c += 32) {
-            const uint32_t b = ql[c];
-            if (c < Pm && b < (uint32_t)HIST_ROWS)
-                atomicAdd(hist + hist_word<C>(b, c), 0x10000u);
-            else
-                atomicAdd(qualg + (size_t)c * 256 + b, 1ull);
-        }
-        if (lane == 0) {
-            Acc a = {0, 0, 0, 0};
-            account_record<C>(a, lenh, p, Ls, Lq);
-            if (a.n_bases) atomicAdd(p.stats + 1, a.n_bases);
-            if (a.clip_seq) atomicAdd(p.stats + 2, a.clip_seq);
-            if (a.clip_qual) atomicAdd(p.stats + 3, a.clip_qual);
-        }
-    }
-    return nl[3];
-}
-
-// ------------------------------------------------------------------------------------------
-// records: one pass = 4 records per warp, 8 lanes each
-// lane = 8*sub + i.  In round T lane (sub,i) owns the 4-byte group g = i + 8T of its record's
-// sequence and quality lines and visits its bytes in the order (k + sub) & 3, k = 0..3, so that
-// the k-th ATOMS of the round touches position 4g + ((k+sub)&3): over the 32 lanes these are 32
-// different residues mod 32 = 32 different banks of hist[chunk][byte][position % 32].
-// ------------------------------------------------------------------------------------------
-struct LaneConst {         // fixed per lane for the whole kernel
-    uint32_t hk[4];        // shared address of hist[0][0][pk[k]]
-    uint32_t wsel[4];      // dp4a weights: 128 in the byte lane visited k-th
-    uint32_t pk[4];        // position visited by the k-th bump in round 0
-};
-
 struct TileView {          // warp-uniform view of the tile being consumed
     const uint8_t* tile;
     const uint16_t* list;
@@ -286,66 +89,6 @@ struct TileView {          // warp-uniform view of the tile being consumed
     uint32_t nstored;        // list entries stored
     uint32_t j0;             // first list entry after which a record starts
     uint32_t own_end;        // tile offset of the end of the owned range
-};
-
-struct RoundCtx {
-    uint32_t as0, aq0;     // shared addresses of the aligned words holding position 4i of seq / qual
-    uint32_t shs, shq;     // funnel shifts that realign them
-    uint32_t ns, nq;       // bytes of seq / qual that have a shared-memory column
-    uint32_t nmax_w, nmin_w;
-    unsigned long long *gseq, *gqual;   // global rows (non-ASCII bytes only)
-};
-
-template <class C, bool ASCII, int T>
-struct Rounds {
-    static __device__ __forceinline__ void run(const RoundCtx& c, const LaneConst& lc)
-    {
-        if (32u * T >= c.nmax_w) return;                                  // warp-uniform
-        const uint32_t s0 = lds32<32 * T>(c.as0), s1 = lds32<32 * T + 4>(c.as0);
-        const uint32_t q0 = lds32<32 * T>(c.aq0), q1 = lds32<32 * T + 4>(c.aq0);
-        const uint32_t vs = __funnelshift_r(s0, s1, c.shs);
-        const uint32_t vq = __funnelshift_r(q0, q1, c.shq);
-        constexpr int CO = 4 * C::CHUNK_WORDS * T;                        // byte offset of chunk T
-        if (ASCII && 32u * (T + 1) <= c.nmin_w) {                         // every lane's group lies inside both lines
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
-                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t pos = lc.pk[k] + 32u * T;
-                if (pos < c.ns) {
-                    if (ASCII) {
-                        red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
-                    } else {
-                        const uint32_t bs = (vs >> (8u * (lc.pk[k] & 3u))) & 0xFFu;
-                        if (bs < (uint32_t)HIST_ROWS)
-                            red_add<CO>(lc.hk[k] + bs * 128u, 1u);
-                        else
-                            atomicAdd(c.gseq + (size_t)pos * 256 + bs, 1ull);
-                    }
-                }
-                if (pos < c.nq) {
-                    if (ASCII) {
-                        red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
-                    } else {
-                        const uint32_t bq = (vq >> (8u * (lc.pk[k] & 3u))) & 0xFFu;
-                        if (bq < (uint32_t)HIST_ROWS)
-                            red_add<CO>(lc.hk[k] + bq * 128u, 0x10000u);
-                        else
-                            atomicAdd(c.gqual + (size_t)pos * 256 + bq, 1ull);
-                    }
-                }
-            }
-        }
-        Rounds<C, ASCII, T + 1>::run(c, lc);
-    }
-};
-template <class C, bool ASCII>
-struct Rounds<C, ASCII, C::NCHUNK> {
-    static __device__ __forceinline__ void run(const RoundCtx&, const LaneConst&) {}
 };
 
 template <class C, bool ASCII>
@@ -422,24 +165,6 @@ __device__ __forceinline__ void records_pass(const ScanParams& p, const TileView
     }
 }
 
-// warp-exclusive prefix of small per-lane counts (most are 0, a few 1 or 2): ballot levels
-__device__ __forceinline__ uint32_t small_prefix(int c, uint32_t lt_mask)
-{
-    const unsigned b1 = __ballot_sync(0xffffffffu, c > 0);
-    const unsigned b2 = __ballot_sync(0xffffffffu, c > 1);
-    const unsigned b3 = __ballot_sync(0xffffffffu, c > 2);
-    uint32_t pre = (uint32_t)__popc(b1 & lt_mask) + (uint32_t)__popc(b2 & lt_mask);
-    if (b3) {
-        pre += (uint32_t)__popc(b3 & lt_mask);
-        for (int lvl = 3;; ++lvl) {
-            const unsigned b = __ballot_sync(0xffffffffu, c > lvl);
-            if (!b) break;
-            pre += (uint32_t)__popc(b & lt_mask);
-        }
-    }
-    return pre;
-}
-
 // line ends of the owned range of a dense-newline tile (more than the list holds; never a healthy
 // FASTQ), ranked straight into the index by one warp
 template <class C>
@@ -465,37 +190,6 @@ __device__ __noinline__ void index_dense(uint32_t* idx_out, unsigned long long i
 }
 
 // ------------------------------------------------------------------------------------------
-// phase inference at the start of a CTA range (one warp): which list entry j0 in 0..3 is followed by
-// a record start?  lane = 8 * candidate + r tests record r of the candidate: '@' after entry j,
-// '+' after entry j + 2, equal raw lengths.  Accepted only if exactly one candidate passes all the
-// records it could test (at least two).  Returns j0, or 4 when the range start is ambiguous.
-// ------------------------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ uint32_t infer_j0(const uint8_t* tile, const uint16_t* list, uint32_t nstored, int lane)
-{
-    const uint32_t cand = (uint32_t)lane >> 3, r = (uint32_t)lane & 7u;
-    const uint32_t j = cand + 4u * r;
-    const bool testable = j + 4u < nstored;
-    bool good = true;
-    if (testable) {
-        const uint32_t s = (uint32_t)list[j] + 1u, h = list[j + 1], q = list[j + 2], pp = list[j + 3], e = list[j + 4];
-        good = tile[s] == '@' && tile[q + 1] == '+' && (e - pp) == (q - h);
-    }
-    const unsigned tested = __ballot_sync(0xffffffffu, testable);
-    const unsigned bad = __ballot_sync(0xffffffffu, testable && !good);
-    uint32_t pass = 0, npass = 0;
-#pragma unroll
-    for (uint32_t c = 0; c < 4; ++c) {
-        const unsigned m = 0xFFu << (8 * c);
-        if (__popc(tested & m) >= 2 && !(bad & m)) {
-            pass = c;
-            ++npass;
-        }
-    }
-    return npass == 1 ? pass : 4u;
-}
-
-// ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <class C>
@@ -513,13 +207,13 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint8_t* stage_mem = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4;
 
-    // launch 1 infers the range phases; launch 2 (F_BASES) runs only when the inference failed;
-    // launch 3 (F_BASES | F_RERUN) only when a bad record was found, restricted to the records before it
+    // launch 1 runs only when the speculative kernel did not deliver; launch 2 (F_RERUN) only when a
+    // bad record was found, restricted to the records before it
     unsigned long long limit = NONE64;
     if (p.flags & F_RERUN) {
         limit = p.res->first_bad;                 // written by the earlier launches, stable during this one
         if (limit == NONE64) return;
-    } else if ((p.flags & F_BASES) && !p.res->spec_fail) {
+    } else if (!p.res->spec_fail) {
         return;
     }
     if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
@@ -547,10 +241,6 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     }
     const unsigned long long tile0 = (unsigned long long)blockIdx.x * p.tiles_per_cta;
     const int K = tile0 < ntiles_eff ? (int)min((unsigned long long)p.tiles_per_cta, ntiles_eff - tile0) : 0;
-    // the range of CTA 0 starts at the shard start, whose line number the caller gave; the others
-    // infer theirs unless the exact bases are there
-    const bool infer = blockIdx.x != 0 && !(p.flags & F_BASES);
-    const bool staged_index = !(p.flags & F_BASES);          // ranks relative to the range -> index_stage
     const bool want_index = (p.flags & F_INDEX) && !(p.flags & F_RERUN) && p.index != nullptr && p.index_cap != 0;
 
     auto tile_no = [&](int k) -> uint32_t { return (uint32_t)tile0 + (uint32_t)k; };
@@ -585,9 +275,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
         // warp sw owns the units [sw * ITERS, (sw + 1) * ITERS) of every tile
         // =====================================================================================
         const int sw = warp - 1;
-        unsigned long long lbase = blockIdx.x == 0 ? line_base : ((p.flags & F_BASES) ? p.ranges[blockIdx.x].base : 0ull);
-        unsigned long long lrank = 0;
-        uint32_t spec_phase = 0, spec_flags = 0;
+        unsigned long long lbase = K ? p.ranges[blockIdx.x].base : 0ull;   // exact line number of the range start
         const int sthreads = C::SW * 32;
         const int stid = sw * 32 + lane;
         const int u0 = sw * C::ITERS;
@@ -664,7 +352,6 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                 own_count_t = __reduce_add_sync(0xffffffffu, o);
                 if (lane == 0) {
                     sc.meta.base = lbase;
-                    sc.meta.lrank = lrank;
                     sc.meta.ts = ts;
                     sc.meta.front = f;
                     sc.meta.own_count = own_count_t;
@@ -700,40 +387,11 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     ubase += call[it];
                 }
             }
-            if (infer && k == 0) {
-                // the first tile of the range: its complete list decides the phase of the whole range
-                __syncwarp();
-                named_bar(1, sthreads);
-                if (sw == 0) {
-                    const uint32_t nstored = min(f + sc.meta.total_count, (uint32_t)C::LIST_CAP);
-                    const uint32_t j0 = infer_j0<C>(tile, list, nstored, lane);
-                    spec_flags = j0 < 4u ? 1u : 2u;
-                    // entry j ends line base - f + j; a record starts after every line = 3 (mod 4)
-                    spec_phase = (3u + f - (j0 & 3u)) & 3u;
-                    lbase = spec_phase;
-                    if (lane == 0) {
-                        sc.meta.base = lbase;
-                        if (j0 >= 4u) atomicExch(&p.res->spec_fail, 1);
-                    }
-                }
-            }
-            if (sw == 0) {
-                lbase += own_count_t;
-                lrank += own_count_t;
-            }
+            if (sw == 0) lbase += own_count_t;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sc.scanned);
             if (stid == 0) trace_ev(p, k, 3);
             if (lane == 0) trace_ev(p, k, 10, true);
-        }
-        if (sw == 0 && lane == 0 && !(p.flags & F_RERUN)) {
-            // what fq_verify_kernel needs: the newline count of the range and the inferred phase
-            RangeInfo& ri = p.ranges[blockIdx.x];
-            ri.count = lrank;
-            if (!(p.flags & F_BASES)) {
-                ri.spec_phase = spec_phase;
-                ri.flags = spec_flags;
-            }
         }
     } else {
         // =====================================================================================
@@ -774,11 +432,9 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
             const uint32_t nrec = tv.nown > tv.j0 ? (tv.nown - tv.j0 + 3u) / 4u : 0u;
             const uint32_t npass = (nrec + 3u) / 4u;
             const uint32_t first = (uint32_t)((hw + C::HW - (k % C::HW)) % C::HW);
-            // where the line ends of this tile go: ranks relative to the range into the staging area of
-            // this CTA, or (exact bases) straight into the caller's index
-            uint32_t* const idx_out = staged_index ? p.index_stage + (size_t)blockIdx.x * p.stage_share : p.index;
-            const unsigned long long idx_cap = staged_index ? p.stage_share : p.index_cap;
-            const unsigned long long idx_base = staged_index ? mk.lrank : mk.base - line_base;
+            uint32_t* const idx_out = p.index;
+            const unsigned long long idx_cap = p.index_cap;
+            const unsigned long long idx_base = mk.base - line_base;   // buffer-local number of the first own line
             const unsigned long long off_base = p.stream_offset + mk.ts;
             if (hw == 0 && lane == 0 && nrec) {
                 // u16 counter halves: when the CTA-wide record count passes the mark, every record warp
@@ -805,8 +461,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                             const unsigned long long gi = idx_base + i;
                             if (gi < idx_cap) idx_out[gi] = (uint32_t)(off_base + (uint32_t)tv.list[tv.f + i] - FRONT);
                         }
-                        // a staging share too small for this range: the exact second launch writes the index
-                        if (staged_index && lane == 0 && idx_base + mk.own_count > idx_cap) atomicExch(&p.res->spec_fail, 1);
+
                     }
                 }
             } else {
@@ -821,10 +476,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
                     }
                 }
                 if (want_index && first == (uint32_t)(1 % C::HW))
-                {
                     index_dense<C>(idx_out, idx_cap, tv.tile, mk.own_count, idx_base, off_base, lane);
-                    if (staged_index && lane == 0 && idx_base + mk.own_count > idx_cap) atomicExch(&p.res->spec_fail, 1);
-                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sc.freed);
