@@ -60,6 +60,7 @@ struct fqb_ctx {
     uint64_t* d_seqraw = nullptr;
     DevResult* d_res = nullptr;
     RangeInfo* d_ranges = nullptr;
+    StreamRange* d_sranges = nullptr;
     uint32_t* d_index_stage = nullptr;  // speculative launch: per-range staging of the line ends
     size_t index_stage_cap = 0;
     unsigned long long* d_linecount = nullptr;
@@ -170,11 +171,13 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->num_sms = prop.multiProcessorCount;
     CKC(scan_configure());
+    CKC(stream_configure());
     ctx->grid = ctx->num_sms * scan_blocks_per_sm(ctx->nchunk);
     CKC(cudaMalloc(&ctx->d_stats, ctx->nwords * 8));
     CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
     CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
     CKC(cudaMalloc(&ctx->d_ranges, sizeof(RangeInfo) * ctx->grid));
+    CKC(cudaMalloc(&ctx->d_sranges, sizeof(StreamRange) * ctx->grid * 32));
     CKC(cudaMalloc(&ctx->d_linecount, 8));
     CKC(cudaMalloc(&ctx->d_carry, sizeof(DevCarry)));
     CKC(cudaHostAlloc(&ctx->h_res, sizeof(DevResult), cudaHostAllocDefault));
@@ -222,6 +225,7 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_seqraw);
     cudaFree(ctx->d_res);
     cudaFree(ctx->d_ranges);
+    cudaFree(ctx->d_sranges);
     cudaFree(ctx->d_index_stage);
     cudaFree(ctx->d_linecount);
     cudaFree(ctx->d_carry);
@@ -235,10 +239,11 @@ void fqb_destroy(fqb_ctx* ctx)
 }
 
 // Enqueue the whole parse of one shard on `st`:
-//   reset -> scan (K1+K2; every CTA range infers its line phase) -> verify -> [reset + scan with the
-//   exact range bases, only if an inference failed] -> diagnose -> [reset + scan again, restricted to
-//   records before the first bad one: each() delivers exactly those, src/lib.rs:226-237]
-//   -> index compaction -> finalize
+//   reset -> speculative kernel (fq_stream.cu) + verification of its record chains
+//   -> [only if that did not deliver: reset, newline counts of the CTA ranges, exact kernel (fq_scan.cu)]
+//   -> diagnose -> [only if a bad record was found: reset + exact kernel again, restricted to the
+//   records before it: each() delivers exactly those, src/lib.rs:226-237]
+//   -> index compaction (speculative kernel only) -> finalize
 static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, DevCarry* carry, uint64_t* total,
                          bool timed)
 {
@@ -250,14 +255,30 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     const uint64_t ntiles64 = (sh->n_own + tile_bytes - 1) / tile_bytes;
     if (ntiles64 > 0xFFFFFFF0ull) return FQB_E_ARG;
     const bool want_index = (sh->flags & FQB_F_INDEX) && sh->d_index && sh->index_cap;
-    if (want_index && sh->index_cap > ctx->index_stage_cap) {
-        if (ctx->d_index_stage) {
-            CK(cudaStreamSynchronize(st));
-            CK(cudaFree(ctx->d_index_stage));
-            ctx->d_index_stage = nullptr;
+    // the speculative kernel: 32 warp ranges per CTA, at least 8 KiB each; every range stages its line
+    // ends in its own share of a staging area sized for lines of >= 16 bytes on average (a range that
+    // needs more gives up and the exact path writes the index)
+    const bool fast = ctx->nchunk <= 5 && !getenv("FQB_NO_FAST");
+    uint64_t srange_bytes, stage_share = 0;
+    {
+        const uint64_t nr = (uint64_t)ctx->grid * 32;
+        srange_bytes = ((sh->n_own + nr - 1) / nr + 15) / 16 * 16;
+        if (srange_bytes < 8192) srange_bytes = 8192;
+        const uint64_t live = (sh->n_own + srange_bytes - 1) / srange_bytes;
+        if (fast && want_index) {
+            stage_share = srange_bytes / 16 + 64;
+            const uint64_t need = live * stage_share;
+            if (need > ctx->index_stage_cap) {
+                if (ctx->d_index_stage) {
+                    CK(cudaStreamSynchronize(st));
+                    CK(cudaFree(ctx->d_index_stage));
+                    ctx->d_index_stage = nullptr;
+                    ctx->index_stage_cap = 0;
+                }
+                CK(cudaMalloc(&ctx->d_index_stage, need * 4 + 64));
+                ctx->index_stage_cap = need;
+            }
         }
-        CK(cudaMalloc(&ctx->d_index_stage, sh->index_cap * 4 + 64));
-        ctx->index_stage_cap = sh->index_cap;
     }
     ScanParams p;
     memset(&p, 0, sizeof p);
@@ -275,10 +296,9 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.ranges = ctx->d_ranges;
     p.nranges = (uint32_t)ctx->grid;
     p.index_stage = ctx->d_index_stage;
-    {
-        const uint64_t live = p.tiles_per_cta ? (ntiles64 + p.tiles_per_cta - 1) / p.tiles_per_cta : 1;
-        p.stage_share = want_index ? sh->index_cap / (live ? live : 1) : 0;
-    }
+    p.sranges = ctx->d_sranges;
+    p.srange_bytes = srange_bytes;
+    p.stage_share = stage_share;
     p.index = sh->d_index;
     p.index_cap = sh->index_cap;
     p.res = ctx->d_res;
@@ -287,13 +307,18 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, 1);
+    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, fast ? 0 : 1);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
     ctx->launches += 1;
     if (p.ntiles) {
         if (timed) CK(cudaEventRecord(ctx->ev0, st));
+        // speculative kernel + the check of its record chains
+        if (fast) {
+            CK(launch_stream(p, carry, ctx->grid, st));
+            ctx->launches += 2;
+        }
         // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
         // of the CTA ranges -> exact line numbers -> exact kernel
         CK(launch_rerun_reset(p, 0, st));
@@ -311,6 +336,10 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         p2.trace = nullptr;
         CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
         ctx->launches += 7;
+        if (fast && want_index) {
+            CK(launch_stream_compact(p, carry, ctx->grid, st));
+            ctx->launches += 1;
+        }
     }
     CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), st));
     ctx->launches += 1;
@@ -350,6 +379,7 @@ int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
             fclose(f);
         }
     }
+    if (getenv("FQB_DEBUG")) fprintf(stderr, "fastq_b200: spec_fail=%d status=%d\n", ctx->h_res->spec_fail, ctx->h_res->status);
     fill_result(ctx->h_res, ctx->last_off, res);
     return FQB_OK;
 }

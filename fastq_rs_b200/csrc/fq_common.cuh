@@ -45,6 +45,16 @@ struct RangeInfo {
     uint32_t flags;                 // 1 = inferred, 2 = inference failed (ambiguous or nothing to test)
 };
 
+// one contiguous byte range = the work of one warp of the speculative kernel (fq_stream.cu)
+struct StreamRange {
+    unsigned long long first;       // buffer offset of the first record that starts in the range (inferred)
+    unsigned long long end;         // cursor after the last such record = start of the first one beyond the range
+    unsigned long long n_lines;     // '\n' of those records inside the owned bytes (+ the ones in front of range 0's first record)
+    unsigned long long rank0;       // prefix of n_lines (fq_stream_verify_kernel): where the staged line ends go
+    uint32_t flags;                 // 1 = delivered, 2 = gave up
+    uint32_t pad;
+};
+
 // streaming carry block (device resident, lives across chunk launches)
 struct DevCarry {
     unsigned long long line_base;   // lines before the next chunk
@@ -68,7 +78,9 @@ struct ScanParams {
     RangeInfo* ranges;              // [nranges] CTA ranges of the exact kernel
     uint32_t nranges;
     uint32_t pad;
-    uint32_t* index_stage;          // speculative run: CTA b stages its line ends at index_stage + b * stage_share
+    StreamRange* sranges;           // [32 * grid] warp ranges of the speculative kernel
+    unsigned long long srange_bytes;
+    uint32_t* index_stage;          // speculative kernel: range r stages its line ends at index_stage + r * stage_share
     unsigned long long stage_share;
     uint32_t* index;
     unsigned long long index_cap;
@@ -94,7 +106,10 @@ cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t s
 cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st);
 cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges, unsigned long long range_bytes,
                                cudaStream_t st);
-cudaError_t launch_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+size_t stream_smem_bytes();
+cudaError_t stream_configure();
+cudaError_t launch_stream(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);
 cudaError_t launch_synth_fixed(uint8_t* out, unsigned long long n, unsigned long long byte_off, uint32_t L,

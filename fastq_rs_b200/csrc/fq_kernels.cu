@@ -153,23 +153,6 @@ __global__ void fq_range_prefix_kernel(const ScanParams p, const DevCarry* carry
     }
 }
 
-// move the staged line ends of every range to their place in the caller's index (only when the
-// speculative launch stands; the exact launch writes the index directly)
-__global__ void fq_index_compact_kernel(const ScanParams p, DevCarry* carry)
-{
-    if (p.res->spec_fail) return;
-    if (carry && carry->status != 0) return;
-    const unsigned long long line_base = carry ? carry->line_base : p.line_base;
-    const int b = blockIdx.x;
-    if ((unsigned long long)b * p.tiles_per_cta >= p.ntiles) return;
-    const RangeInfo ri = p.ranges[b];
-    const uint32_t* src = p.index_stage + (size_t)b * p.stage_share;
-    const unsigned long long dst0 = ri.base - line_base;
-    const unsigned long long stride = (unsigned long long)gridDim.y * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.y * blockDim.x + threadIdx.x; i < ri.count; i += stride)
-        if (dst0 + i < p.index_cap) p.index[dst0 + i] = src[i];
-}
-
 // fold the raw sequence-byte histogram into the six base classes (validate_dnan's alphabet,
 // src/records.rs:29-33), publish the outcome, and (streaming) add the chunk into the totals
 __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned long long* total)
@@ -376,12 +359,6 @@ cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges
     fq_range_count_kernel<<<dim3(nranges, 8), 256, 0, st>>>(p, carry, range_bytes);
     if (cudaGetLastError() != cudaSuccess) return cudaGetLastError();
     fq_range_prefix_kernel<<<1, 32, 0, st>>>(p, carry, nranges);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
-{
-    fq_index_compact_kernel<<<dim3(grid, 8), 256, 0, st>>>(p, carry);
     return cudaGetLastError();
 }
 

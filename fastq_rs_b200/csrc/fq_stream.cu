@@ -1,0 +1,519 @@
+// fq_stream.cu -- the SPECULATIVE sm_100a scan kernel (K1 delimit + K2 per-position histograms):
+// 32 autonomous warps per SM, each streaming through its own contiguous byte range the way the
+// reference's Buffer does (src/buffer.rs:30-100, src/lib.rs:255-303) -- load a window at the cursor,
+// delimit the complete records in it, consume them, move the cursor to the first record that did not
+// fit -- with no synchronisation between warps at all:
+//
+//   window      one TMA bulk copy (UBLKCP, 4 KB, 16-byte aligned source) into the warp's own buffer,
+//               completing on the warp's own mbarrier
+//   scan        16-byte SWAR newline masks (3 ops / word + dp4a bit gather), warp prefix of the
+//               counts, line starts into a u16 list in shared memory
+//   records     8 lanes per record: '@' / '+' / raw-length validation (src/records.rs:201-247), then
+//               the histogram rounds of fq_hist.cuh (one dp4a + one ATOMS per byte, bank-conflict free)
+//   index       the line ends of the window, ranked relative to the range, into a staging area
+//
+// What makes it speculative: a range other than the first does not know where its first record
+// starts.  It INFERS it -- of four consecutive line starts exactly one is a record start; the warp
+// tests the four candidates against the grammar over the following records and takes the only one
+// that holds -- and fq_stream_verify_kernel afterwards checks that the record chain of every range
+// ends exactly where the next range started.  Chained from the first range, whose start is known,
+// that proves the ranges saw the very records a sequential parse delivers.  Anything else --
+// a record that fails validation, a record longer than the window, bytes >= 0x80, an ambiguous or
+// mis-inferred start, a staging area too small -- only raises res->spec_fail, and the exact path
+// (fq_scan.cu) redoes the shard.  Results never depend on the inference.
+#include "fq_hist.cuh"
+
+namespace fq {
+
+template <int NCHUNK_>
+struct SCfg {
+    static constexpr int NCHUNK = NCHUNK_;
+    static constexpr int PPAD = 32 * NCHUNK;
+    static constexpr int CHUNK_WORDS = HIST_ROWS * 32;
+    static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;
+    static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
+    static constexpr int WIN = 4096;                       // window bytes
+    static constexpr int NU = WIN / UNIT;                  // 512-byte units per window
+    static constexpr int LIST_N = 192;                     // u16 entries: [0] = cursor, [j] = start of the line after the j-th '\n'
+    static constexpr int MAXR = (LIST_N - 12) / 4;         // records consumed per window at most
+    static constexpr int LIST_DUMMY = LIST_N - 1;          // writes beyond the capacity land here
+    static constexpr int WARP_BYTES = WIN + 16 + LIST_N * 2;
+    static constexpr int TAIL_PAD = 256;                   // word loads of the rounds may run past the last buffer
+    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + 32 * WARP_BYTES + TAIL_PAD;
+    static_assert(WARP_BYTES % 16 == 0, "TMA destination alignment");
+};
+
+struct Window {
+    unsigned long long src;   // buffer-relative offset of the window (16-byte aligned)
+    uint32_t pad;             // cursor - src
+    uint32_t vlen;            // valid bytes in the window
+};
+
+// ------------------------------------------------------------------------------------------
+// window load: the analogue of Buffer::clean + read_into, src/buffer.rs:51-100 -- nothing is moved,
+// the next window simply starts at the 16-byte boundary below the first record that did not fit
+// ------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, unsigned long long* bar, uint32_t& parity,
+                                           unsigned long long cur, int lane)
+{
+    Window w;
+    w.src = cur & ~15ull;
+    w.pad = (uint32_t)(cur - w.src);
+    w.vlen = (uint32_t)min((unsigned long long)C::WIN, p.n_avail - w.src);
+    const uint32_t bulk = w.vlen & ~15u;
+    __syncwarp();
+    if (lane == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, bulk);
+        if (bulk) bulk_g2s(buf, p.data + w.src, bulk, bar);
+    }
+    // the bytes the 16-byte-granular bulk copy leaves out (last window of the shard only)
+    if ((w.vlen & 15u) && (uint32_t)lane < (w.vlen & 15u)) buf[bulk + lane] = p.data[w.src + bulk + lane];
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    __syncwarp();
+    return w;
+}
+
+// newline masks of the window (bit 7 + i of mask[it] = byte i of the lane's piece of unit `it`),
+// restricted to [pad, vlen); returns the newline count, hib = OR of all words
+template <class C>
+__device__ __forceinline__ uint32_t win_scan(const uint8_t* buf, const Window& w, uint32_t (&mask)[C::NU],
+                                             uint32_t (&call)[C::NU], uint32_t& hib, int lane)
+{
+    uint32_t total = 0;
+    hib = 0;
+#pragma unroll
+    for (int it = 0; it < C::NU; ++it) {
+        const uint32_t off = (uint32_t)it * UNIT + (uint32_t)lane * 16u;
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + off);
+        hib |= v.x | v.y | v.z | v.w;
+        uint32_t mm = nlmask16s7(v);
+        if (it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
+        if (w.vlen < (uint32_t)C::WIN) {                                    // stale bytes beyond the data
+            const int rem = (int)w.vlen - (int)off;
+            const uint32_t m = rem >= 16 ? 0xFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+            mm &= m << 7;
+        }
+        mask[it] = mm;
+        call[it] = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm));
+        total += call[it];
+    }
+    return total;
+}
+
+// line starts of the window: list[0] = cursor, list[j] = position after the j-th '\n'
+template <class C>
+__device__ __forceinline__ void win_list(uint16_t* list, const Window& w, const uint32_t (&mask)[C::NU],
+                                         const uint32_t (&call)[C::NU], int lane, uint32_t lt_mask)
+{
+    if (lane == 0) list[0] = (uint16_t)w.pad;
+    uint32_t ubase = 1;
+#pragma unroll
+    for (int it = 0; it < C::NU; ++it) {
+        const uint32_t mm = mask[it];
+        const int c = __popc(mm);
+        const uint32_t rank = ubase + small_prefix(c, lt_mask);
+        const uint32_t pos1 = (uint32_t)it * UNIT + (uint32_t)lane * 16u - 7u + 1u;   // bit -> position + 1
+        // the first and the last newline of the piece, no loop; a third one is rare
+        if (c > 0) list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(mm) - 1u);
+        if (c > 1) list[min(rank + (uint32_t)c - 1u, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + 31u - (uint32_t)__clz(mm));
+        if (__any_sync(0xffffffffu, c > 2) && c > 2) {
+            uint32_t m2 = mm & (mm - 1u), r2 = rank + 1u;
+            while (m2 & (m2 - 1u)) {
+                list[min(r2, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(m2) - 1u);
+                m2 &= m2 - 1u;
+                ++r2;
+            }
+        }
+        ubase += call[it];
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// where does the first record of the range start?  list[c], c in 1..4, are four consecutive line
+// starts: lane = 8 * (c - 1) + r tests record r of candidate c ('@' at its start, '+' after its
+// sequence line, equal raw lengths).  Accepted only if exactly one candidate passes every record it
+// could test, at least two.  Returns c, or 0 when the start is ambiguous.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t infer_start(const uint8_t* buf, const uint16_t* list, uint32_t nstored, int lane)
+{
+    const uint32_t cand = 1u + ((uint32_t)lane >> 3), r = (uint32_t)lane & 7u;
+    const uint32_t j = cand + 4u * r;
+    const bool testable = j + 4u <= nstored;
+    bool good = true;
+    if (testable) {
+        const uint32_t s = list[j], h = list[j + 1] - 1u, q = list[j + 2] - 1u, pp = list[j + 3] - 1u, e = list[j + 4] - 1u;
+        good = buf[s] == '@' && buf[q + 1] == '+' && (e - pp) == (q - h);
+    }
+    const unsigned tested = __ballot_sync(0xffffffffu, testable);
+    const unsigned bad = __ballot_sync(0xffffffffu, testable && !good);
+    uint32_t pass = 0, npass = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c) {
+        const unsigned m = 0xFFu << (8 * c);
+        if (__popc(tested & m) >= 2 && !(bad & m)) {
+            pass = c + 1u;
+            ++npass;
+        }
+    }
+    return npass == 1 ? pass : 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// one pass = 4 records, 8 lanes each (same lane mapping as the exact kernel; see fq_hist.cuh)
+// ------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s, const uint16_t* list,
+                                            const LaneConst& lc, uint32_t* lenh, uint32_t n_rec, uint32_t pass, Acc& acc,
+                                            int lane)
+{
+    const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
+    const uint32_t r = 4u * pass + sub;
+    const bool valid = r < n_rec;
+    const uint16_t* lp = list + 4u * min(r, (uint32_t)C::MAXR);
+    const uint32_t l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3], l4 = lp[4];
+    // stale entries must not turn into wild shared-memory addresses in the rounds below
+    const uint32_t s = valid ? l0 : 0u, h = valid ? l1 - 1u : 0u, q = valid ? l2 - 1u : 1u, pp = valid ? l3 - 1u : 0u,
+                   e = valid ? l4 - 1u : 1u;
+    const uint32_t c_at = buf[s], c_plus = buf[q + 1], c_sr = buf[q - 1], c_qr = buf[e - 1];
+    // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
+    const bool ok = valid && c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
+    if (ok && i == 0) acc.n_records++;
+    if (p.flags & F_HIST) {
+        const uint32_t P = p.max_len;
+        const uint32_t Pm = P < (uint32_t)C::PPAD ? P : (uint32_t)C::PPAD;
+        uint32_t Ls = 0, Lq = 0;
+        if (ok) {
+            const uint32_t Lr = q - h - 1u;
+            // seq()/qual() drop one trailing '\r' (src/records.rs:65-73,82-90)
+            Ls = Lr - ((Lr > 0 && c_sr == '\r') ? 1u : 0u);
+            Lq = Lr - ((Lr > 0 && c_qr == '\r') ? 1u : 0u);
+            if (i == 0) account_record<C>(acc, lenh, p, Ls, Lq);
+        }
+        RoundCtx c;
+        c.ns = min(Ls, Pm);
+        c.nq = min(Lq, Pm);
+        c.nmax_w = __reduce_max_sync(0xffffffffu, max(c.ns, c.nq));
+        c.nmin_w = __reduce_min_sync(0xffffffffu, min(c.ns, c.nq));
+        const uint32_t sa = h + 1u + 4u * i;                // shared offset of position 4i of the sequence line
+        const uint32_t qa = pp + 1u + 4u * i;
+        c.as0 = buf_s + (sa & ~3u);
+        c.aq0 = buf_s + (qa & ~3u);
+        c.shs = (sa & 3u) * 8u;
+        c.shq = (qa & 3u) * 8u;
+        c.gseq = p.seqraw;
+        c.gqual = p.stats + stats_qual_off(P);
+        Rounds<C, true, 0>::run(c, lc);
+        // positions beyond the shared-memory columns but below P: straight to global (P > PPAD only)
+        if (P > Pm && ok) {
+            const uint32_t gs = min(Ls, P), gq = min(Lq, P);
+            for (uint32_t g = Pm + i; g < gs; g += 8) atomicAdd(c.gseq + (size_t)g * 256 + buf[h + 1u + g], 1ull);
+            for (uint32_t g = Pm + i; g < gq; g += 8) atomicAdd(c.gqual + (size_t)g * 256 + buf[pp + 1u + g], 1ull);
+        }
+    }
+    return __any_sync(0xffffffffu, valid && !ok);
+}
+
+struct StreamCta {
+    uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
+    uint32_t flush_epoch;
+};
+
+template <class C>
+__global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* lenh = hist + C::HIST_WORDS;
+    __shared__ unsigned long long bars[32];
+    __shared__ StreamCta cta;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    if (p.res->spec_fail) return;                              // the host sent this shard to the exact path
+    if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
+    const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
+
+    for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += 1024) hist[i] = 0;
+    if (lane == 0) mbar_init(&bars[warp], 1);
+    if (tid == 0) {
+        cta.recs = 0;
+        cta.flush_epoch = 0;
+    }
+    fence_mbar_init();
+    __syncthreads();
+
+    uint8_t* buf = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4 + warp * C::WARP_BYTES;
+    uint16_t* list = reinterpret_cast<uint16_t*>(buf + C::WIN + 16);
+    const uint32_t buf_s = smem_u32(buf);
+    unsigned long long* bar = &bars[warp];
+    uint32_t parity = 0;
+
+    LaneConst lc;
+    {
+        const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
+            lc.pk[kk] = 4u * i + bytek;
+            lc.hk[kk] = smem_u32(hist) + 4u * lc.pk[kk];
+            lc.wsel[kk] = 128u << (8u * bytek);
+        }
+    }
+
+    // the range of this warp: records that START in [R0, R1)
+    const uint32_t rid = blockIdx.x * 32u + (uint32_t)warp;
+    const unsigned long long R0 = (unsigned long long)rid * p.srange_bytes;
+    const bool live = R0 < p.n_own;
+    const unsigned long long R1 = live ? min(p.n_own, R0 + p.srange_bytes) : 0ull;
+    const bool want_index = (p.flags & F_INDEX) && p.index != nullptr && p.index_cap != 0;
+    uint32_t* const idx_out = p.index_stage + (size_t)rid * p.stage_share;
+
+    Acc acc = {0, 0, 0, 0};
+    unsigned long long cur = 0, first = NONE64, lrank = 0;
+    bool failed = false;
+    uint32_t my_epoch = 0;
+    constexpr int SLICE = (C::HIST_WORDS + 31) / 32;
+
+    if (live) {
+        // ---- where the first record of the range starts -------------------------------------------
+        bool need_window = true;
+        uint32_t known = 0;                                  // range 0: the caller's line number decides
+        if (rid == 0) {
+            const bool line_start = (p.flags & F_LINE_START) || ((p.flags & F_FRONT16) && p.data[-1] == '\n');
+            const uint32_t phase = (uint32_t)(line_base & 3ull);
+            if (line_start && phase == 0) {
+                need_window = false;                         // byte 0 starts a record
+                cur = 0;
+            } else {
+                known = 4u - phase;                          // the record starts after the known-th '\n' of the shard
+            }
+        }
+        if (need_window) {
+            // ranges other than the first look at the byte in front of them too: it may be the '\n'
+            // that makes R0 itself a line start
+            const unsigned long long c0 = rid == 0 ? 0ull : R0 - 1ull;
+            const Window w = win_load<C>(p, buf, bar, parity, c0, lane);
+            uint32_t mask[C::NU], call[C::NU], hib;
+            const uint32_t total = win_scan<C>(buf, w, mask, call, hib, lane);
+            win_list<C>(list, w, mask, call, lane, lt_mask);
+            const uint32_t nstored = min(total, (uint32_t)C::LIST_N - 2u);
+            uint32_t c = 0;
+            if (rid == 0)
+                c = known <= nstored ? known : 0u;
+            else
+                c = infer_start(buf, list, nstored, lane);
+            if (c == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                failed = true;
+            } else {
+                cur = w.src + list[c];
+                if (rid == 0) {
+                    // the line ends in front of the first record belong to the shard all the same
+                    if (want_index && lane < (int)c) {
+                        if ((unsigned long long)lane < p.stage_share)
+                            idx_out[lane] = (uint32_t)(p.stream_offset + w.src + list[lane + 1] - 1u);
+                        else
+                            failed = true;
+                    }
+                    failed = __any_sync(0xffffffffu, failed);
+                    if (w.src + list[c] - 1u >= p.n_own) failed = true;   // (a shard inside one record)
+                    lrank = c;
+                }
+            }
+        }
+        first = cur;
+
+        // ---- stream through the range ------------------------------------------------------------
+        while (!failed && cur < R1 && cur < p.n_avail) {
+            const Window w = win_load<C>(p, buf, bar, parity, cur, lane);
+            uint32_t mask[C::NU], call[C::NU], hib;
+            const uint32_t total = win_scan<C>(buf, w, mask, call, hib, lane);
+            const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
+            if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
+                break;
+            }
+            win_list<C>(list, w, mask, call, lane, lt_mask);
+            // records of the window that start inside the range (their starts increase)
+            uint32_t n_rec;
+            {
+                const uint32_t ra = (uint32_t)lane, rb = (uint32_t)lane + 32u;
+                const bool va = ra < n_win && w.src + list[4u * ra] < R1;
+                const bool vb = rb < n_win && w.src + list[4u * min(rb, (uint32_t)C::MAXR)] < R1;
+                n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
+            }
+            bool bad = false;
+            for (uint32_t pass = 0; 4u * pass < n_rec; ++pass)
+                bad |= stream_pass<C>(p, buf, buf_s, list, lc, lenh, n_rec, pass, acc, lane);
+            if (bad) {
+                failed = true;   // a record that fails validation: the exact path finds and classifies it
+                break;
+            }
+            // line ends of the consumed records that lie in the owned bytes of the shard
+            uint32_t n_lines = 4u * n_rec;
+            if (w.src + list[n_lines] - 1u >= p.n_own) {       // the shard's last record reaches beyond n_own
+                const bool in = lane < 4 && w.src + list[n_lines - 3u + (uint32_t)lane] - 1u < p.n_own;
+                n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (want_index) {
+                if (lrank + n_lines > p.stage_share) {
+                    failed = true;   // staging share too small: the exact path writes the index
+                    break;
+                }
+                const unsigned long long off = p.stream_offset + w.src - 1ull;
+                for (uint32_t j = lane; j < n_lines; j += 32) idx_out[lrank + j] = (uint32_t)(off + list[j + 1u]);
+            }
+            lrank += n_lines;
+            cur = w.src + list[4u * n_rec];
+            // u16 counter halves: whoever pushes the CTA-wide record count over a multiple of the mark
+            // starts a drain epoch; every warp drains its slice when it notices
+            if (lane == 0) {
+                const uint32_t before = atomicAdd(&cta.recs, n_rec);
+                if (before / 24000u != (before + n_rec) / 24000u) atomicAdd(&cta.flush_epoch, 1u);
+            }
+            const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(&cta.flush_epoch);
+            if (ep != my_epoch) {
+                my_epoch = ep;
+                flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
+            }
+            if (n_rec < n_win) break;                           // the next record belongs to the next range
+        }
+        // data that ends inside the owned bytes without a record boundary: not a clean shard
+        if (!failed && cur < R1) failed = true;
+        if (lane == 0) {
+            StreamRange& sr = p.sranges[rid];
+            sr.first = first;
+            sr.end = cur;
+            sr.n_lines = lrank;
+            sr.flags = failed ? 2u : 1u;
+            if (failed) atomicExch(&p.res->spec_fail, 1);
+        }
+    }
+
+    // ---- drain -----------------------------------------------------------------------------
+    __syncthreads();
+    flush_hist<C>(hist, p, 0, C::HIST_WORDS, tid, 1024);
+    {
+        unsigned long long* lenh_g = p.stats + stats_len_off(p.max_len);
+        for (int i = tid; i < C::PPAD + 2; i += 1024) {
+            const uint32_t v = lenh[i];
+            if (v) atomicAdd(lenh_g + i, (unsigned long long)v);
+        }
+    }
+    acc.n_records = warp_sum_u64(acc.n_records);
+    acc.n_bases = warp_sum_u64(acc.n_bases);
+    acc.clip_seq = warp_sum_u64(acc.clip_seq);
+    acc.clip_qual = warp_sum_u64(acc.clip_qual);
+    if (lane == 0) {
+        if (acc.n_records) atomicAdd(p.stats + 0, acc.n_records);
+        if (acc.n_bases) atomicAdd(p.stats + 1, acc.n_bases);
+        if (acc.clip_seq) atomicAdd(p.stats + 2, acc.clip_seq);
+        if (acc.clip_qual) atomicAdd(p.stats + 3, acc.clip_qual);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// verify: the record chain of every range must end exactly where the next range started, and the
+// last one at (or, with more of the stream following, beyond) the end of the owned bytes.  Also the
+// prefix of the per-range line counts = where each range's staged line ends go.  One 1024-thread block.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams p, const DevCarry* carry)
+{
+    __shared__ unsigned long long part[1024];
+    __shared__ int fail_s;
+    if (p.res->spec_fail) return;
+    if (carry && carry->status != 0) return;
+    const unsigned long long line_base = carry ? carry->line_base : p.line_base;
+    const int t = threadIdx.x;
+    const uint32_t nlive = (uint32_t)((p.n_own + p.srange_bytes - 1) / p.srange_bytes);
+    const uint32_t per = (nlive + 1023u) / 1024u;
+    if (t == 0) fail_s = 0;
+    __syncthreads();
+    unsigned long long sum = 0;
+    int fail = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t r = (uint32_t)t * per + k;
+        if (r >= nlive) break;
+        const StreamRange sr = p.sranges[r];
+        sum += sr.n_lines;
+        if (sr.flags != 1u) fail = 1;
+        if (r + 1 < nlive) {
+            if (p.sranges[r + 1].first != sr.end) fail = 1;
+        } else if (sr.end < p.n_own || ((p.flags & F_EOF) && sr.end != p.n_avail)) {
+            fail = 1;
+        }
+    }
+    part[t] = sum;
+    if (fail) fail_s = 1;
+    __syncthreads();
+    // exclusive prefix over the 1024 partial sums (Hillis-Steele)
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = t >= d ? part[t - d] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - sum;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t r = (uint32_t)t * per + k;
+        if (r >= nlive) break;
+        p.sranges[r].rank0 = run;
+        run += p.sranges[r].n_lines;
+    }
+    if (t == 1023) {
+        p.res->n_lines = part[1023];
+        p.res->line_end = line_base + part[1023];
+    }
+    if (t == 0 && fail_s) p.res->spec_fail = 1;
+}
+
+// move the staged line ends of every range to their place in the caller's index (only when the
+// speculative launch stands; the exact kernel writes the index directly)
+__global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams p, const DevCarry* carry)
+{
+    if (p.res->spec_fail) return;
+    if (carry && carry->status != 0) return;
+    const uint32_t nlive = (uint32_t)((p.n_own + p.srange_bytes - 1) / p.srange_bytes);
+    for (uint32_t r = blockIdx.x; r < nlive; r += gridDim.x) {
+        const StreamRange sr = p.sranges[r];
+        const uint32_t* src = p.index_stage + (size_t)r * p.stage_share;
+        for (unsigned long long i = threadIdx.x; i < sr.n_lines; i += blockDim.x)
+            if (sr.rank0 + i < p.index_cap) p.index[sr.rank0 + i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+using SCfg5 = SCfg<5>;
+
+size_t stream_smem_bytes() { return (size_t)SCfg5::TOTAL; }
+uint32_t stream_window_bytes() { return (uint32_t)SCfg5::WIN; }
+
+cudaError_t stream_configure()
+{
+    return cudaFuncSetAttribute(fq_stream_kernel<SCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg5::TOTAL);
+}
+
+cudaError_t launch_stream(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+{
+    fq_stream_kernel<SCfg5><<<grid, 1024, SCfg5::TOTAL, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    fq_stream_verify_kernel<<<1, 1024, 0, st>>>(p, carry);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+{
+    fq_stream_compact_kernel<<<grid * 8, 256, 0, st>>>(p, carry);
+    return cudaGetLastError();
+}
+
+}  // namespace fq
