@@ -43,6 +43,32 @@ struct SCfg {
     static_assert(WARP_BYTES % 16 == 0, "TMA destination alignment");
 };
 
+// The two masks of the newline test live in constant memory so that ptxas keeps them in registers /
+// constant-bank operands: (w ^ A) & B is then ONE LOP3 instead of two with immediates.
+static __constant__ uint32_t fq_kmask[2] = {0x0A0A0A0Au, 0x7F7F7F7Fu};
+
+// 0x80 in every byte of w that equals '\n' (exact), 3 instructions: LOP3, IADD, LOP3
+__device__ __forceinline__ uint32_t nlbits3(uint32_t w, uint32_t kA, uint32_t kB)
+{
+    uint32_t y;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(y) : "r"(w), "r"(kA), "r"(kB));   // (w ^ A) & B
+    const uint32_t t = y + kB;
+    return ~(t | w) & 0x80808080u;
+}
+// newline mask of a 16-byte piece, shifted left by 7 (see nlmask16s7)
+__device__ __forceinline__ uint32_t nlmask16k(const uint4& v, uint32_t kA, uint32_t kB)
+{
+    const uint32_t m0 = nlbits3(v.x, kA, kB), m1 = nlbits3(v.y, kA, kB), m2 = nlbits3(v.z, kA, kB), m3 = nlbits3(v.w, kA, kB);
+    const uint32_t lo = dp4a_u(m1, 0x80402010u, dp4a_u(m0, 0x08040201u, 0u));
+    const uint32_t hi = dp4a_u(m3, 0x80402010u, dp4a_u(m2, 0x08040201u, 0u));
+    return lo + (hi << 8);
+}
+
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+
 struct Window {
     unsigned long long src;   // buffer-relative offset of the window (16-byte aligned)
     uint32_t pad;             // cursor - src
@@ -76,60 +102,67 @@ __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, un
     return w;
 }
 
-// newline masks of the window (bit 7 + i of mask[it] = byte i of the lane's piece of unit `it`),
-// restricted to [pad, vlen); returns the newline count, hib = OR of all words
-template <class C>
-__device__ __forceinline__ uint32_t win_scan(const uint8_t* buf, const Window& w, uint32_t (&mask)[C::NU],
-                                             uint32_t (&call)[C::NU], uint32_t& hib, int lane)
+// One pass over the window: newline masks, ranks and the list of line starts
+//   list[0] = cursor, list[j] = position after the j-th '\n' of [pad, vlen)
+// The ranks need no second pass: the running count is warp-local.  Per 512-byte unit the per-lane
+// counts (0, 1, rarely 2) are prefix-summed with two ballots; a piece with three or more newlines
+// sends the unit through the generic path.  Returns the newline count; hib = OR of all words.
+// RAGGED: the window is shorter than WIN (the end of the shard) -- stale bytes are masked out.
+template <class C, bool RAGGED>
+__device__ __forceinline__ uint32_t win_scan_t(const uint8_t* buf, uint16_t* list, const Window& w, uint32_t& hib,
+                                               int lane, uint32_t lt_mask)
 {
-    uint32_t total = 0;
+    const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
+    if (lane == 0) list[0] = (uint16_t)w.pad;
+    uint32_t ubase = 1;
     hib = 0;
+    const uint32_t list_s = smem_u32(list);
+    const uint32_t lane_pos = (uint32_t)lane * 16u - 7u + 1u;              // bit index -> position + 1
 #pragma unroll
     for (int it = 0; it < C::NU; ++it) {
         const uint32_t off = (uint32_t)it * UNIT + (uint32_t)lane * 16u;
         const uint4 v = *reinterpret_cast<const uint4*>(buf + off);
         hib |= v.x | v.y | v.z | v.w;
-        uint32_t mm = nlmask16s7(v);
+        uint32_t mm = nlmask16k(v, kA, kB);                                 // bit 7 + i = byte i of the piece
         if (it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
-        if (w.vlen < (uint32_t)C::WIN) {                                    // stale bytes beyond the data
+        if (RAGGED) {                                                       // stale bytes beyond the data
             const int rem = (int)w.vlen - (int)off;
             const uint32_t m = rem >= 16 ? 0xFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
             mm &= m << 7;
         }
-        mask[it] = mm;
-        call[it] = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mm));
-        total += call[it];
-    }
-    return total;
-}
-
-// line starts of the window: list[0] = cursor, list[j] = position after the j-th '\n'
-template <class C>
-__device__ __forceinline__ void win_list(uint16_t* list, const Window& w, const uint32_t (&mask)[C::NU],
-                                         const uint32_t (&call)[C::NU], int lane, uint32_t lt_mask)
-{
-    if (lane == 0) list[0] = (uint16_t)w.pad;
-    uint32_t ubase = 1;
-#pragma unroll
-    for (int it = 0; it < C::NU; ++it) {
-        const uint32_t mm = mask[it];
         const int c = __popc(mm);
-        const uint32_t rank = ubase + small_prefix(c, lt_mask);
-        const uint32_t pos1 = (uint32_t)it * UNIT + (uint32_t)lane * 16u - 7u + 1u;   // bit -> position + 1
-        // the first and the last newline of the piece, no loop; a third one is rare
-        if (c > 0) list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(mm) - 1u);
-        if (c > 1) list[min(rank + (uint32_t)c - 1u, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + 31u - (uint32_t)__clz(mm));
-        if (__any_sync(0xffffffffu, c > 2) && c > 2) {
-            uint32_t m2 = mm & (mm - 1u), r2 = rank + 1u;
-            while (m2 & (m2 - 1u)) {
-                list[min(r2, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(m2) - 1u);
-                m2 &= m2 - 1u;
-                ++r2;
+        const unsigned b1 = __ballot_sync(0xffffffffu, mm != 0);
+        const unsigned b2 = __ballot_sync(0xffffffffu, c > 1);
+        const unsigned b3 = __ballot_sync(0xffffffffu, c > 2);
+        const uint32_t pos1 = (uint32_t)it * UNIT + lane_pos;
+        if (!b3) {
+            const uint32_t rank = min(ubase + (uint32_t)__popc(b1 & lt_mask) + (uint32_t)__popc(b2 & lt_mask),
+                                      (uint32_t)C::LIST_DUMMY - 1u);
+            const uint32_t a = list_s + 2u * rank;
+            // the first and the last newline of the piece: lowest and highest set bit
+            if (mm != 0) sts16(a, pos1 + (uint32_t)__clz(__brev(mm)));
+            if (c > 1) sts16(a + 2u, pos1 + 31u - (uint32_t)__clz(mm));
+            ubase += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
+        } else {
+            uint32_t rank = ubase + small_prefix(c, lt_mask);
+            while (mm) {
+                list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(mm) - 1u);
+                mm &= mm - 1u;
+                ++rank;
             }
+            ubase += __reduce_add_sync(0xffffffffu, (uint32_t)c);
         }
-        ubase += call[it];
     }
     __syncwarp();
+    return ubase - 1u;
+}
+
+template <class C>
+__device__ __forceinline__ uint32_t win_scan(const uint8_t* buf, uint16_t* list, const Window& w, uint32_t& hib,
+                                             int lane, uint32_t lt_mask)
+{
+    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true>(buf, list, w, hib, lane, lt_mask);
+    return win_scan_t<C, false>(buf, list, w, hib, lane, lt_mask);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -165,59 +198,114 @@ __device__ __forceinline__ uint32_t infer_start(const uint8_t* buf, const uint16
 // ------------------------------------------------------------------------------------------
 // one pass = 4 records, 8 lanes each (same lane mapping as the exact kernel; see fq_hist.cuh)
 // ------------------------------------------------------------------------------------------
+struct WinAcc {   // per-lane sums over one window, folded into the CTA counters once per window
+    uint32_t n_records, n_bases;
+};
+
+struct LaneK {    // fixed per lane for the whole kernel (see LaneConst; positions are implied by hk)
+    uint32_t hk[4];        // shared address of hist[0][0][position visited k-th in round 0]
+    uint32_t wsel[4];      // dp4a weights: 128 in the byte lane visited k-th
+};
+
+template <class C, int T>
+struct SRounds {
+    // inc_s / inc_q: 1 / 0x10000 for lanes with a record, 0 for the others (their bumps add nothing)
+    static __device__ __forceinline__ void run(uint32_t as0, uint32_t aq0, uint32_t shs, uint32_t shq, uint32_t ns,
+                                               uint32_t nq, uint32_t nmax_w, uint32_t nmin_w, uint32_t inc_s,
+                                               uint32_t inc_q, uint32_t hist_s, const LaneK& lc)
+    {
+        if (32u * T >= nmax_w) return;                                    // warp-uniform
+        const uint32_t s0 = lds32<32 * T>(as0), s1 = lds32<32 * T + 4>(as0);
+        const uint32_t q0 = lds32<32 * T>(aq0), q1 = lds32<32 * T + 4>(aq0);
+        const uint32_t vs = __funnelshift_r(s0, s1, shs);
+        const uint32_t vq = __funnelshift_r(q0, q1, shq);
+        constexpr int CO = 4 * C::CHUNK_WORDS * T;                        // byte offset of chunk T
+        if (32u * (T + 1) <= nmin_w) {                                    // every record's group lies inside both lines
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), inc_s);
+                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), inc_q);
+            }
+        } else {
+            // position visited k-th = (hk[k] - hist_s) / 4; it lies in the line iff it is below the bytes
+            // the line has left for this round
+            const int ts = (int)hist_s + 4 * ((int)ns - 32 * T), tq = (int)hist_s + 4 * ((int)nq - 32 * T);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((int)lc.hk[k] < ts) red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
+                if ((int)lc.hk[k] < tq) red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
+            }
+        }
+        SRounds<C, T + 1>::run(as0, aq0, shs, shq, ns, nq, nmax_w, nmin_w, inc_s, inc_q, hist_s, lc);
+    }
+};
+template <class C>
+struct SRounds<C, C::NCHUNK> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                                               uint32_t, uint32_t, uint32_t, uint32_t, const LaneK&)
+    {
+    }
+};
+
+// returns true if a record of the pass failed validation
 template <class C>
 __device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s, const uint16_t* list,
-                                            const LaneConst& lc, uint32_t* lenh, uint32_t n_rec, uint32_t pass, Acc& acc,
-                                            int lane)
+                                            const LaneK& lc, uint32_t hist_s, uint32_t* lenh, uint32_t Pm,
+                                            uint32_t n_rec, uint32_t pass, WinAcc& wa, int lane)
 {
     const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
     const uint32_t r = 4u * pass + sub;
     const bool valid = r < n_rec;
-    const uint16_t* lp = list + 4u * min(r, (uint32_t)C::MAXR);
-    const uint32_t l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3], l4 = lp[4];
-    // stale entries must not turn into wild shared-memory addresses in the rounds below
-    const uint32_t s = valid ? l0 : 0u, h = valid ? l1 - 1u : 0u, q = valid ? l2 - 1u : 1u, pp = valid ? l3 - 1u : 0u,
-                   e = valid ? l4 - 1u : 1u;
+    // lanes without a record look at record 0 of the window (real data, harmless) and are masked out below
+    const uint16_t* lp = list + (valid ? 4u * r : 0u);
+    const uint32_t s = lp[0], h = lp[1] - 1u, q = lp[2] - 1u, pp = lp[3] - 1u, e = lp[4] - 1u;
     const uint32_t c_at = buf[s], c_plus = buf[q + 1], c_sr = buf[q - 1], c_qr = buf[e - 1];
     // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
-    const bool ok = valid && c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
-    if (ok && i == 0) acc.n_records++;
+    const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
+    const bool ok = valid && good;
     if (p.flags & F_HIST) {
-        const uint32_t P = p.max_len;
-        const uint32_t Pm = P < (uint32_t)C::PPAD ? P : (uint32_t)C::PPAD;
         uint32_t Ls = 0, Lq = 0;
         if (ok) {
             const uint32_t Lr = q - h - 1u;
             // seq()/qual() drop one trailing '\r' (src/records.rs:65-73,82-90)
             Ls = Lr - ((Lr > 0 && c_sr == '\r') ? 1u : 0u);
             Lq = Lr - ((Lr > 0 && c_qr == '\r') ? 1u : 0u);
-            if (i == 0) account_record<C>(acc, lenh, p, Ls, Lq);
+            if (i == 0) {
+                wa.n_records++;
+                wa.n_bases += Ls;
+                if (max(Ls, Lq) > p.max_len) {                              // longer than the tracked positions: rare
+                    if (Ls > p.max_len) atomicAdd(p.stats + 2, (unsigned long long)(Ls - p.max_len));
+                    if (Lq > p.max_len) atomicAdd(p.stats + 3, (unsigned long long)(Lq - p.max_len));
+                }
+                if (Ls > p.max_len)
+                    atomicAdd(p.stats + stats_len_off(p.max_len) + p.max_len + 1, 1ull);
+                else
+                    atomicAdd(lenh + Ls, 1u);
+            }
         }
-        RoundCtx c;
-        c.ns = min(Ls, Pm);
-        c.nq = min(Lq, Pm);
-        c.nmax_w = __reduce_max_sync(0xffffffffu, max(c.ns, c.nq));
-        c.nmin_w = __reduce_min_sync(0xffffffffu, min(c.ns, c.nq));
-        const uint32_t sa = h + 1u + 4u * i;                // shared offset of position 4i of the sequence line
-        const uint32_t qa = pp + 1u + 4u * i;
-        c.as0 = buf_s + (sa & ~3u);
-        c.aq0 = buf_s + (qa & ~3u);
-        c.shs = (sa & 3u) * 8u;
-        c.shq = (qa & 3u) * 8u;
-        c.gseq = p.seqraw;
-        c.gqual = p.stats + stats_qual_off(P);
-        Rounds<C, true, 0>::run(c, lc);
+        const uint32_t ns = min(Ls, Pm), nq = min(Lq, Pm);
+        const uint32_t nmax_w = __reduce_max_sync(0xffffffffu, max(ns, nq));
+        // lanes without a record do not hold the fast rounds back: their bumps add zero
+        const uint32_t nmin_w = __reduce_min_sync(0xffffffffu, ok ? min(ns, nq) : 0xFFFFFFFFu);
+        const uint32_t sa = buf_s + h + 1u + 4u * i;       // shared address of position 4i of the sequence line
+        const uint32_t qa = buf_s + pp + 1u + 4u * i;      // (buf_s is 16-byte aligned; the funnel shift takes sa * 8 mod 32)
+        SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, nmax_w, nmin_w, ok ? 1u : 0u, ok ? 0x10000u : 0u,
+                           hist_s, lc);
         // positions beyond the shared-memory columns but below P: straight to global (P > PPAD only)
-        if (P > Pm && ok) {
-            const uint32_t gs = min(Ls, P), gq = min(Lq, P);
-            for (uint32_t g = Pm + i; g < gs; g += 8) atomicAdd(c.gseq + (size_t)g * 256 + buf[h + 1u + g], 1ull);
-            for (uint32_t g = Pm + i; g < gq; g += 8) atomicAdd(c.gqual + (size_t)g * 256 + buf[pp + 1u + g], 1ull);
+        if (p.max_len > Pm && ok) {
+            const uint32_t gs = min(Ls, p.max_len), gq = min(Lq, p.max_len);
+            unsigned long long* gqual = p.stats + stats_qual_off(p.max_len);
+            for (uint32_t g = Pm + i; g < gs; g += 8) atomicAdd(p.seqraw + (size_t)g * 256 + buf[h + 1u + g], 1ull);
+            for (uint32_t g = Pm + i; g < gq; g += 8) atomicAdd(gqual + (size_t)g * 256 + buf[pp + 1u + g], 1ull);
         }
+    } else if (ok && i == 0) {
+        wa.n_records++;
     }
-    return __any_sync(0xffffffffu, valid && !ok);
+    return __any_sync(0xffffffffu, valid && !good);
 }
 
 struct StreamCta {
+    unsigned long long n_records, n_bases;   // totals of the CTA
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
     uint32_t flush_epoch;
 };
@@ -243,6 +331,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += 1024) hist[i] = 0;
     if (lane == 0) mbar_init(&bars[warp], 1);
     if (tid == 0) {
+        cta.n_records = 0;
+        cta.n_bases = 0;
         cta.recs = 0;
         cta.flush_epoch = 0;
     }
@@ -255,14 +345,14 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     unsigned long long* bar = &bars[warp];
     uint32_t parity = 0;
 
-    LaneConst lc;
+    const uint32_t hist_s = smem_u32(hist);
+    LaneK lc;
     {
         const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
-            lc.pk[kk] = 4u * i + bytek;
-            lc.hk[kk] = smem_u32(hist) + 4u * lc.pk[kk];
+            lc.hk[kk] = hist_s + 4u * (4u * i + bytek);
             lc.wsel[kk] = 128u << (8u * bytek);
         }
     }
@@ -273,10 +363,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     const bool live = R0 < p.n_own;
     const unsigned long long R1 = live ? min(p.n_own, R0 + p.srange_bytes) : 0ull;
     const bool want_index = (p.flags & F_INDEX) && p.index != nullptr && p.index_cap != 0;
-    uint32_t* const idx_out = p.index_stage + (size_t)rid * p.stage_share;
 
-    Acc acc = {0, 0, 0, 0};
-    unsigned long long cur = 0, first = NONE64, lrank = 0;
+    unsigned long long cur = 0, lrank = 0;
     bool failed = false;
     uint32_t my_epoch = 0;
     constexpr int SLICE = (C::HIST_WORDS + 31) / 32;
@@ -300,9 +388,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             // that makes R0 itself a line start
             const unsigned long long c0 = rid == 0 ? 0ull : R0 - 1ull;
             const Window w = win_load<C>(p, buf, bar, parity, c0, lane);
-            uint32_t mask[C::NU], call[C::NU], hib;
-            const uint32_t total = win_scan<C>(buf, w, mask, call, hib, lane);
-            win_list<C>(list, w, mask, call, lane, lt_mask);
+            uint32_t hib;
+            const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
             const uint32_t nstored = min(total, (uint32_t)C::LIST_N - 2u);
             uint32_t c = 0;
             if (rid == 0)
@@ -317,7 +404,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                     // the line ends in front of the first record belong to the shard all the same
                     if (want_index && lane < (int)c) {
                         if ((unsigned long long)lane < p.stage_share)
-                            idx_out[lane] = (uint32_t)(p.stream_offset + w.src + list[lane + 1] - 1u);
+                            p.index_stage[(size_t)rid * p.stage_share + lane] = (uint32_t)(p.stream_offset + w.src + list[lane + 1] - 1u);
                         else
                             failed = true;
                     }
@@ -327,37 +414,48 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                 }
             }
         }
-        first = cur;
+        if (lane == 0) p.sranges[rid].first = cur;
 
         // ---- stream through the range ------------------------------------------------------------
+        const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
         while (!failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, cur, lane);
-            uint32_t mask[C::NU], call[C::NU], hib;
-            const uint32_t total = win_scan<C>(buf, w, mask, call, hib, lane);
+            uint32_t hib;
+            const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
             const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
             if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                 failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
                 break;
             }
-            win_list<C>(list, w, mask, call, lane, lt_mask);
-            // records of the window that start inside the range (their starts increase)
-            uint32_t n_rec;
-            {
+            // records of the window that start inside the range (their starts increase); everything
+            // below is relative to the window
+            uint32_t n_rec = n_win;
+            const unsigned long long room = R1 - w.src;          // > pad
+            if (room < (unsigned long long)C::WIN) {              // the range ends inside this window
                 const uint32_t ra = (uint32_t)lane, rb = (uint32_t)lane + 32u;
-                const bool va = ra < n_win && w.src + list[4u * ra] < R1;
-                const bool vb = rb < n_win && w.src + list[4u * min(rb, (uint32_t)C::MAXR)] < R1;
+                const bool va = ra < n_win && list[4u * ra] < (uint32_t)room;
+                const bool vb = rb < n_win && list[4u * min(rb, (uint32_t)C::MAXR)] < (uint32_t)room;
                 n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
             }
             bool bad = false;
+            WinAcc wa = {0, 0};
             for (uint32_t pass = 0; 4u * pass < n_rec; ++pass)
-                bad |= stream_pass<C>(p, buf, buf_s, list, lc, lenh, n_rec, pass, acc, lane);
+                bad |= stream_pass<C>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
             if (bad) {
                 failed = true;   // a record that fails validation: the exact path finds and classifies it
                 break;
             }
+            {
+                const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
+                if (lane == 0) {
+                    atomicAdd(&cta.n_records, (unsigned long long)nr);
+                    atomicAdd(&cta.n_bases, (unsigned long long)nb);
+                }
+            }
             // line ends of the consumed records that lie in the owned bytes of the shard
             uint32_t n_lines = 4u * n_rec;
-            if (w.src + list[n_lines] - 1u >= p.n_own) {       // the shard's last record reaches beyond n_own
+            const uint32_t next = list[n_lines];                  // start of the first record not consumed
+            if (w.src + next - 1u >= p.n_own) {                   // the shard's last record reaches beyond n_own
                 const bool in = lane < 4 && w.src + list[n_lines - 3u + (uint32_t)lane] - 1u < p.n_own;
                 n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
             }
@@ -366,11 +464,12 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                     failed = true;   // staging share too small: the exact path writes the index
                     break;
                 }
-                const unsigned long long off = p.stream_offset + w.src - 1ull;
-                for (uint32_t j = lane; j < n_lines; j += 32) idx_out[lrank + j] = (uint32_t)(off + list[j + 1u]);
+                const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;   // low 32 bits are what the index holds
+                uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
+                for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + list[j + 1u];
             }
             lrank += n_lines;
-            cur = w.src + list[4u * n_rec];
+            cur = w.src + next;
             // u16 counter halves: whoever pushes the CTA-wide record count over a multiple of the mark
             // starts a drain epoch; every warp drains its slice when it notices
             if (lane == 0) {
@@ -382,13 +481,12 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                 my_epoch = ep;
                 flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
             }
-            if (n_rec < n_win) break;                           // the next record belongs to the next range
+            if (n_rec < n_win) break;                             // the next record belongs to the next range
         }
         // data that ends inside the owned bytes without a record boundary: not a clean shard
         if (!failed && cur < R1) failed = true;
         if (lane == 0) {
             StreamRange& sr = p.sranges[rid];
-            sr.first = first;
             sr.end = cur;
             sr.n_lines = lrank;
             sr.flags = failed ? 2u : 1u;
@@ -406,15 +504,9 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             if (v) atomicAdd(lenh_g + i, (unsigned long long)v);
         }
     }
-    acc.n_records = warp_sum_u64(acc.n_records);
-    acc.n_bases = warp_sum_u64(acc.n_bases);
-    acc.clip_seq = warp_sum_u64(acc.clip_seq);
-    acc.clip_qual = warp_sum_u64(acc.clip_qual);
-    if (lane == 0) {
-        if (acc.n_records) atomicAdd(p.stats + 0, acc.n_records);
-        if (acc.n_bases) atomicAdd(p.stats + 1, acc.n_bases);
-        if (acc.clip_seq) atomicAdd(p.stats + 2, acc.clip_seq);
-        if (acc.clip_qual) atomicAdd(p.stats + 3, acc.clip_qual);
+    if (tid == 0) {
+        if (cta.n_records) atomicAdd(p.stats + 0, cta.n_records);
+        if (cta.n_bases) atomicAdd(p.stats + 1, cta.n_bases);
     }
 }
 
