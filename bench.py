@@ -5,7 +5,7 @@
 
 A step = one pass of the hot path over one batch of synthetic 150 bp FASTQ (SURVEY.md 8(d),
 input A): newline / record-boundary scan with '@'/'+' validation, the line-end index, and the
-per-position ACGTN + quality-byte histograms, fused in one sm_100a kernel.
+per-position ACGTN + quality-byte histograms, fused in one sm_100a kernel (fq_stream.cu).
 
   value     whole-job GB/s with the bytes already resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the host API (fqb_parse_host): pinned host bytes -> H2D -> kernels
@@ -240,7 +240,7 @@ def run_ours(args):
     k_ms = float(np.mean(scan_ms))
     alg_bytes = n_own + 16 * (n_own // REC_BYTES)            # 1 B read per input byte + 16 B index per record
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fq_scan_kernel<5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5>>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": args.traffic_bytes, "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes}
 

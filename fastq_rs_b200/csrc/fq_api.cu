@@ -313,21 +313,23 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
     ctx->launches += 1;
     if (p.ntiles) {
-        if (timed) CK(cudaEventRecord(ctx->ev0, st));
-        // speculative kernel + the check of its record chains
+        // speculative kernel + the check of its record chains (the events bracket the dominant kernel:
+        // the speculative one, or the exact one when the speculative one is not used for this shape)
         if (fast) {
-            CK(launch_stream(p, carry, ctx->grid, st));
+            if (timed) CK(cudaEventRecord(ctx->ev0, st));
+            CK(launch_stream(p, ctx->grid, st));
+            if (timed) CK(cudaEventRecord(ctx->ev1, st));
+            CK(launch_stream_verify(p, carry, st));
             ctx->launches += 2;
         }
         // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
         // of the CTA ranges -> exact line numbers -> exact kernel
         CK(launch_rerun_reset(p, 0, st));
         CK(launch_range_count(p, carry, ctx->grid, (unsigned long long)p.tiles_per_cta * tile_bytes, st));
+        if (timed && !fast) CK(cudaEventRecord(ctx->ev0, st));
         CK(launch_scan(p, ctx->nchunk, ctx->grid, st));
-        if (timed) {
-            CK(cudaEventRecord(ctx->ev1, st));
-            ctx->ev_valid = true;
-        }
+        if (timed && !fast) CK(cudaEventRecord(ctx->ev1, st));
+        if (timed) ctx->ev_valid = true;
         // classify the first bad record; redo restricted to the records before it (each() delivers those)
         CK(launch_diagnose(p, carry, st));
         CK(launch_rerun_reset(p, 1, st));

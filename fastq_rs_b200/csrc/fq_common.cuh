@@ -108,7 +108,8 @@ cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges
                                cudaStream_t st);
 size_t stream_smem_bytes();
 cudaError_t stream_configure();
-cudaError_t launch_stream(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+cudaError_t launch_stream(const ScanParams& p, int grid, cudaStream_t st);
+cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);

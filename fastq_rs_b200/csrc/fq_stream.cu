@@ -593,11 +593,14 @@ cudaError_t stream_configure()
     return cudaFuncSetAttribute(fq_stream_kernel<SCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg5::TOTAL);
 }
 
-cudaError_t launch_stream(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
+cudaError_t launch_stream(const ScanParams& p, int grid, cudaStream_t st)
 {
     fq_stream_kernel<SCfg5><<<grid, 1024, SCfg5::TOTAL, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st)
+{
     fq_stream_verify_kernel<<<1, 1024, 0, st>>>(p, carry);
     return cudaGetLastError();
 }

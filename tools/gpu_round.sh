@@ -10,5 +10,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
    python bench.py --gib 4 --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fq_stream_kernel -s 1 -c 1 -o gpurun_out/scan_full -f \
-   python tools/prof_one.py 4.0 1 1 150 3 > gpurun_out/ncu_full.log 2>&1
+   python tools/prof_one.py 16.0 1 1 150 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/smoke.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench.log; tail -3 gpurun_out/bench_ref.log; tail -5 gpurun_out/ncu_full.log
