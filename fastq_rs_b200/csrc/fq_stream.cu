@@ -305,7 +305,7 @@ __device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* 
 }
 
 struct StreamCta {
-    unsigned long long n_records, n_bases;   // totals of the CTA
+    uint32_t n_records, n_bases;   // totals of the CTA (u32: a CTA sees < 4 G bases per launch; native shared atomics)
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
     uint32_t flush_epoch;
 };
@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
             lc.hk[kk] = hist_s + 4u * (4u * i + bytek);
             lc.wsel[kk] = 128u << (8u * bytek);
+            // keep them in registers: recomputing them inside every pass costs more than it saves
+            asm volatile("" : "+r"(lc.hk[kk]), "+r"(lc.wsel[kk]));
         }
     }
 
@@ -448,8 +450,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             {
                 const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
                 if (lane == 0) {
-                    atomicAdd(&cta.n_records, (unsigned long long)nr);
-                    atomicAdd(&cta.n_bases, (unsigned long long)nb);
+                    atomicAdd(&cta.n_records, nr);
+                    atomicAdd(&cta.n_bases, nb);
                 }
             }
             // line ends of the consumed records that lie in the owned bytes of the shard
@@ -505,8 +507,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
         }
     }
     if (tid == 0) {
-        if (cta.n_records) atomicAdd(p.stats + 0, cta.n_records);
-        if (cta.n_bases) atomicAdd(p.stats + 1, cta.n_bases);
+        if (cta.n_records) atomicAdd(p.stats + 0, (unsigned long long)cta.n_records);
+        if (cta.n_bases) atomicAdd(p.stats + 1, (unsigned long long)cta.n_bases);
     }
 }
 
