@@ -11,12 +11,12 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libfastq_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes (include/fastq_b200.h)
-OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO = range(7)
+OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
 E_ARG, E_STATE, E_NOMEM, E_CUDA = 50, 51, 52, 100
-F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16 = 0x01, 0x02, 0x04, 0x08, 0x10
+F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 MAX_RECORD_BYTES = 68 * 1024
 SYNTH_SEED = 0xFA57A11CE5EED001
 NO_OFFSET = 0xFFFFFFFFFFFFFFFF
@@ -47,7 +47,8 @@ class Shard(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("status", C.c_int32), ("finished", C.c_int32), ("n_records", C.c_uint64),
-                ("n_lines", C.c_uint64), ("err_offset", C.c_uint64), ("tail_offset", C.c_uint64)]
+                ("n_lines", C.c_uint64), ("err_offset", C.c_uint64), ("tail_offset", C.c_uint64),
+                ("line_phase", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def build(force: bool = False) -> str:

@@ -20,7 +20,7 @@ using namespace fq;
 
 namespace {
 
-__global__ void fq_init_kernel(DevResult* r, int spec_fail)
+__global__ void fq_init_kernel(DevResult* r, int spec_fail, int line_phase)
 {
     r->first_bad = NONE64;
     r->tail_start = NONE64;
@@ -31,6 +31,7 @@ __global__ void fq_init_kernel(DevResult* r, int spec_fail)
     r->status = 0;
     r->finished = 0;
     r->spec_fail = spec_fail;   // 1: no speculative launch, go straight to the exact path
+    r->line_phase = line_phase;
 }
 
 struct Slot {  // one stage of the streaming ring
@@ -132,6 +133,7 @@ const char* fqb_strerror(int status)
     case FQB_E_TOO_LONG: return "Fastq record is too long";
     case FQB_E_TRUNCATED: return "Possibly truncated input file";
     case FQB_E_IO: return "I/O error";
+    case FQB_E_PHASE: return "the first record of the shard could not be inferred";
     case FQB_E_ARG: return "invalid argument";
     case FQB_E_STATE: return "call out of order";
     case FQB_E_NOMEM: return "out of memory";
@@ -259,14 +261,17 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     // ends in its own share of a staging area sized for lines of >= 16 bytes on average (a range that
     // needs more gives up and the exact path writes the index)
     const bool fast = ctx->nchunk <= 5 && !getenv("FQB_NO_FAST");
-    uint64_t srange_bytes, stage_share = 0;
+    uint64_t srange_bytes, stage_share = 0, n_sranges;
     {
+        // equal ranges, rounded DOWN to 16 bytes; the last range takes the remainder (a little more work
+        // for one warp, but a range too short to hold a few records could not infer its start)
         const uint64_t nr = (uint64_t)ctx->grid * 32;
-        srange_bytes = ((sh->n_own + nr - 1) / nr + 15) / 16 * 16;
+        srange_bytes = sh->n_own / nr / 16 * 16;
         if (srange_bytes < 8192) srange_bytes = 8192;
-        const uint64_t live = (sh->n_own + srange_bytes - 1) / srange_bytes;
+        const uint64_t live = std::max<uint64_t>(1, std::min<uint64_t>(nr, sh->n_own / srange_bytes));
+        n_sranges = live;
         if (fast && want_index) {
-            stage_share = srange_bytes / 16 + 64;
+            stage_share = 2 * srange_bytes / 16 + 64;
             const uint64_t need = live * stage_share;
             if (need > ctx->index_stage_cap) {
                 if (ctx->d_index_stage) {
@@ -288,7 +293,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.stream_offset = sh->stream_offset;
     p.line_base = sh->line_base;
     p.carry = carry;
-    p.flags = (sh->flags & (F_HIST | F_INDEX | F_LINE_START | F_EOF | F_FRONT16)) | (carry ? F_CARRY : 0);
+    p.flags = (sh->flags & (F_HIST | F_INDEX | F_LINE_START | F_EOF | F_FRONT16 | F_INFER_START)) | (carry ? F_CARRY : 0);
+    if ((p.flags & F_INFER_START) && carry) return FQB_E_ARG;   // a stream knows its line numbers
     if ((p.flags & F_FRONT16) && (p.flags & F_LINE_START)) return FQB_E_ARG;
     p.max_len = ctx->P;
     p.ntiles = (uint32_t)ntiles64;
@@ -298,6 +304,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.index_stage = ctx->d_index_stage;
     p.sranges = ctx->d_sranges;
     p.srange_bytes = srange_bytes;
+    p.n_sranges = (uint32_t)n_sranges;
     p.stage_share = stage_share;
     p.index = sh->d_index;
     p.index_cap = sh->index_cap;
@@ -307,7 +314,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, fast ? 0 : 1);
+    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3));
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
@@ -323,21 +330,24 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             ctx->launches += 2;
         }
         // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
-        // of the CTA ranges -> exact line numbers -> exact kernel
-        CK(launch_rerun_reset(p, 0, st));
-        CK(launch_range_count(p, carry, ctx->grid, (unsigned long long)p.tiles_per_cta * tile_bytes, st));
-        if (timed && !fast) CK(cudaEventRecord(ctx->ev0, st));
-        CK(launch_scan(p, ctx->nchunk, ctx->grid, st));
-        if (timed && !fast) CK(cudaEventRecord(ctx->ev1, st));
-        if (timed) ctx->ev_valid = true;
-        // classify the first bad record; redo restricted to the records before it (each() delivers those)
-        CK(launch_diagnose(p, carry, st));
-        CK(launch_rerun_reset(p, 1, st));
-        ScanParams p2 = p;
-        p2.flags |= F_RERUN;
-        p2.trace = nullptr;
-        CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
-        ctx->launches += 7;
+        // of the CTA ranges -> exact line numbers -> exact kernel.  It needs the exact line_base: with
+        // FQB_F_INFER_START a speculative launch that did not deliver ends in FQB_E_PHASE instead.
+        if (!(p.flags & F_INFER_START)) {
+            CK(launch_rerun_reset(p, 0, st));
+            CK(launch_range_count(p, carry, ctx->grid, (unsigned long long)p.tiles_per_cta * tile_bytes, st));
+            if (timed && !fast) CK(cudaEventRecord(ctx->ev0, st));
+            CK(launch_scan(p, ctx->nchunk, ctx->grid, st));
+            if (timed && !fast) CK(cudaEventRecord(ctx->ev1, st));
+            // classify the first bad record; redo restricted to the records before it (each() delivers those)
+            CK(launch_diagnose(p, carry, st));
+            CK(launch_rerun_reset(p, 1, st));
+            ScanParams p2 = p;
+            p2.flags |= F_RERUN;
+            p2.trace = nullptr;
+            CK(launch_scan(p2, ctx->nchunk, ctx->grid, st));
+            ctx->launches += 7;
+        }
+        if (timed) ctx->ev_valid = fast || !(p.flags & F_INFER_START);
         if (fast && want_index) {
             CK(launch_stream_compact(p, carry, ctx->grid, st));
             ctx->launches += 1;
@@ -363,6 +373,8 @@ static void fill_result(const DevResult* r, uint64_t stream_offset_of_tail_base,
     res->n_lines = r->n_lines;
     res->err_offset = r->err_offset;
     res->tail_offset = r->tail_start == NONE64 ? UINT64_MAX : stream_offset_of_tail_base + r->tail_start;
+    res->line_phase = (uint32_t)r->line_phase;
+    res->reserved = 0;
 }
 
 int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
@@ -635,6 +647,8 @@ static int stream_drain(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
     res->n_lines = ctx->h_carry->n_lines;
     res->err_offset = ctx->h_carry->err_offset;
     res->tail_offset = UINT64_MAX;
+    res->line_phase = 0;
+    res->reserved = 0;
     ctx->streaming = false;
     return FQB_OK;
 }

@@ -19,6 +19,7 @@ constexpr uint32_t MAXREC = 68u * 1024u;   // src/lib.rs:129 BUFSIZE
 constexpr unsigned long long NONE64 = ~0ull;
 
 constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0x08, F_FRONT16 = 0x10;
+constexpr uint32_t F_INFER_START = 0x20;   // the phase of line_base is unknown: range 0 infers its first record too
 constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad
 constexpr uint32_t F_CARRY = 0x200;        // internal: streaming, line_base comes from the carry block
 
@@ -33,8 +34,8 @@ struct DevResult {
     unsigned long long n_records;
     int status;
     int finished;
-    int spec_fail;                  // a CTA range could not infer / mis-inferred its line phase: redo with exact bases
-    int pad;
+    int spec_fail;                  // the speculative kernel did not deliver: the exact path redoes the shard
+    int line_phase;                 // line_base mod 4 implied by the first record start of the shard
 };
 
 // one contiguous range of tiles = the work of one CTA
@@ -77,7 +78,7 @@ struct ScanParams {
     uint32_t tiles_per_cta;         // CTA b owns the tiles [b * tiles_per_cta, (b + 1) * tiles_per_cta)
     RangeInfo* ranges;              // [nranges] CTA ranges of the exact kernel
     uint32_t nranges;
-    uint32_t pad;
+    uint32_t n_sranges;             // live warp ranges: r covers [r * srange_bytes, (r + 1) * srange_bytes), the last one up to n_own
     StreamRange* sranges;           // [32 * grid] warp ranges of the speculative kernel
     unsigned long long srange_bytes;
     uint32_t* index_stage;          // speculative kernel: range r stages its line ends at index_stage + r * stage_share

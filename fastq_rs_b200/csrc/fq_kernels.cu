@@ -190,6 +190,9 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
     if (i0 == 0) {
         DevResult* r = p.res;
         if (!skip) {
+            // an inferred shard start the speculative kernel could not stand by: the caller must come
+            // back with the exact line_base (FQB_E_PHASE)
+            if ((p.flags & F_INFER_START) && r->spec_fail) r->status = 7;
             r->n_records = p.stats[0];
             r->finished = r->status == 0 ? 1 : 0;
             if (carry) {

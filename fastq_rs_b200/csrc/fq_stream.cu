@@ -70,7 +70,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
 }
 
 struct Window {
-    unsigned long long src;   // buffer-relative offset of the window (16-byte aligned)
+    long long src;            // buffer-relative offset of the window (16-byte aligned; -16 for the window that
+                              // looks at the byte in front of the shard)
     uint32_t pad;             // cursor - src
     uint32_t vlen;            // valid bytes in the window
 };
@@ -81,12 +82,12 @@ struct Window {
 // ------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, unsigned long long* bar, uint32_t& parity,
-                                           unsigned long long cur, int lane)
+                                           long long cur, int lane)
 {
     Window w;
-    w.src = cur & ~15ull;
+    w.src = cur & ~15ll;
     w.pad = (uint32_t)(cur - w.src);
-    w.vlen = (uint32_t)min((unsigned long long)C::WIN, p.n_avail - w.src);
+    w.vlen = (uint32_t)min((long long)C::WIN, (long long)p.n_avail - w.src);
     const uint32_t bulk = w.vlen & ~15u;
     __syncwarp();
     if (lane == 0) {
@@ -166,14 +167,16 @@ __device__ __forceinline__ uint32_t win_scan(const uint8_t* buf, uint16_t* list,
 }
 
 // ------------------------------------------------------------------------------------------
-// where does the first record of the range start?  list[c], c in 1..4, are four consecutive line
-// starts: lane = 8 * (c - 1) + r tests record r of candidate c ('@' at its start, '+' after its
+// where does the first record of the range start?  list[cf .. cf + 3] are four consecutive line
+// starts: lane = 8 * (c - cf) + r tests record r of candidate c ('@' at its start, '+' after its
 // sequence line, equal raw lengths).  Accepted only if exactly one candidate passes every record it
-// could test, at least two.  Returns c, or 0 when the start is ambiguous.
+// could test, at least two.  Returns c, or NO_START when the start is ambiguous.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t infer_start(const uint8_t* buf, const uint16_t* list, uint32_t nstored, int lane)
+constexpr uint32_t NO_START = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t infer_start(const uint8_t* buf, const uint16_t* list, uint32_t nstored, uint32_t cf,
+                                                int lane)
 {
-    const uint32_t cand = 1u + ((uint32_t)lane >> 3), r = (uint32_t)lane & 7u;
+    const uint32_t cand = cf + ((uint32_t)lane >> 3), r = (uint32_t)lane & 7u;
     const uint32_t j = cand + 4u * r;
     const bool testable = j + 4u <= nstored;
     bool good = true;
@@ -188,11 +191,11 @@ __device__ __forceinline__ uint32_t infer_start(const uint8_t* buf, const uint16
     for (uint32_t c = 0; c < 4; ++c) {
         const unsigned m = 0xFFu << (8 * c);
         if (__popc(tested & m) >= 2 && !(bad & m)) {
-            pass = c + 1u;
+            pass = cf + c;
             ++npass;
         }
     }
-    return npass == 1 ? pass : 0u;
+    return npass == 1 ? pass : NO_START;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -362,8 +365,9 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     // the range of this warp: records that START in [R0, R1)
     const uint32_t rid = blockIdx.x * 32u + (uint32_t)warp;
     const unsigned long long R0 = (unsigned long long)rid * p.srange_bytes;
-    const bool live = R0 < p.n_own;
-    const unsigned long long R1 = live ? min(p.n_own, R0 + p.srange_bytes) : 0ull;
+    const bool live = rid < p.n_sranges;
+    // (the last range takes the remainder: a range too short to hold a few records could not infer its start)
+    const unsigned long long R1 = live ? (rid + 1u == p.n_sranges ? p.n_own : R0 + p.srange_bytes) : 0ull;
     const bool want_index = (p.flags & F_INDEX) && p.index != nullptr && p.index_cap != 0;
 
     unsigned long long cur = 0, lrank = 0;
@@ -373,46 +377,42 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
-        bool need_window = true;
-        uint32_t known = 0;                                  // range 0: the caller's line number decides
-        if (rid == 0) {
-            const bool line_start = (p.flags & F_LINE_START) || ((p.flags & F_FRONT16) && p.data[-1] == '\n');
-            const uint32_t phase = (uint32_t)(line_base & 3ull);
-            if (line_start && phase == 0) {
-                need_window = false;                         // byte 0 starts a record
-                cur = 0;
-            } else {
-                known = 4u - phase;                          // the record starts after the known-th '\n' of the shard
-            }
-        }
-        if (need_window) {
-            // ranges other than the first look at the byte in front of them too: it may be the '\n'
-            // that makes R0 itself a line start
-            const unsigned long long c0 = rid == 0 ? 0ull : R0 - 1ull;
-            const Window w = win_load<C>(p, buf, bar, parity, c0, lane);
+        {
+            // the window starts one byte early where that byte exists: it may be the '\n' that makes
+            // the range start itself a line start
+            const bool front = rid != 0 || (p.flags & F_FRONT16);
+            const Window w = win_load<C>(p, buf, bar, parity, (long long)R0 - (front ? 1 : 0), lane);
             uint32_t hib;
             const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
             const uint32_t nstored = min(total, (uint32_t)C::LIST_N - 2u);
-            uint32_t c = 0;
-            if (rid == 0)
-                c = known <= nstored ? known : 0u;
-            else
-                c = infer_start(buf, list, nstored, lane);
-            if (c == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+            const uint32_t neg = (front && nstored >= 1u && list[1] == 16u) ? 1u : 0u;   // a '\n' right in front of the range
+            uint32_t c;
+            if (rid != 0 || (p.flags & F_INFER_START)) {
+                c = infer_start(buf, list, nstored, (rid == 0 && (p.flags & F_LINE_START)) ? 0u : 1u, lane);
+            } else {
+                // the caller's line number decides: K owned '\n' lie in front of the first record
+                const bool line_start = (p.flags & F_LINE_START) || neg;
+                const uint32_t phase = (uint32_t)(line_base & 3ull);
+                const uint32_t K = (line_start && phase == 0) ? 0u : 4u - phase;
+                c = K + neg <= nstored ? K + neg : NO_START;
+            }
+            if (c == NO_START || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                 failed = true;
             } else {
-                cur = w.src + list[c];
+                cur = (unsigned long long)(w.src + (long long)list[c]);
                 if (rid == 0) {
-                    // the line ends in front of the first record belong to the shard all the same
-                    if (want_index && lane < (int)c) {
+                    // the K line ends in front of the first record belong to the shard all the same
+                    const uint32_t K = c - neg;
+                    if (want_index && (uint32_t)lane < K) {
                         if ((unsigned long long)lane < p.stage_share)
-                            p.index_stage[(size_t)rid * p.stage_share + lane] = (uint32_t)(p.stream_offset + w.src + list[lane + 1] - 1u);
+                            p.index_stage[lane] = (uint32_t)(p.stream_offset + (unsigned long long)(w.src + (long long)list[neg + 1u + lane] - 1));
                         else
                             failed = true;
                     }
                     failed = __any_sync(0xffffffffu, failed);
-                    if (w.src + list[c] - 1u >= p.n_own) failed = true;   // (a shard inside one record)
-                    lrank = c;
+                    if (K && (unsigned long long)(w.src + (long long)list[c] - 1) >= p.n_own) failed = true;   // (a shard inside one record)
+                    lrank = K;
+                    if (lane == 0) p.res->line_phase = (int)((4u - K) & 3u);
                 }
             }
         }
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
         // ---- stream through the range ------------------------------------------------------------
         const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
         while (!failed && cur < R1 && cur < p.n_avail) {
-            const Window w = win_load<C>(p, buf, bar, parity, cur, lane);
+            const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
             uint32_t hib;
             const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
             const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams
     if (carry && carry->status != 0) return;
     const unsigned long long line_base = carry ? carry->line_base : p.line_base;
     const int t = threadIdx.x;
-    const uint32_t nlive = (uint32_t)((p.n_own + p.srange_bytes - 1) / p.srange_bytes);
+    const uint32_t nlive = p.n_sranges;
     const uint32_t per = (nlive + 1023u) / 1024u;
     if (t == 0) fail_s = 0;
     __syncthreads();
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
 {
     if (p.res->spec_fail) return;
     if (carry && carry->status != 0) return;
-    const uint32_t nlive = (uint32_t)((p.n_own + p.srange_bytes - 1) / p.srange_bytes);
+    const uint32_t nlive = p.n_sranges;
     for (uint32_t r = blockIdx.x; r < nlive; r += gridDim.x) {
         const StreamRange sr = p.sranges[r];
         const uint32_t* src = p.index_stage + (size_t)r * p.stage_share;

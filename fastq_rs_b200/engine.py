@@ -11,8 +11,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (E_HEADER, E_LENGTH, E_SEP, E_TOO_LONG, E_TRUNCATED, F_EOF, F_FRONT16, F_HIST,
-                   F_INDEX, F_LINE_START, OK)
+from ._lib import (E_HEADER, E_LENGTH, E_PHASE, E_SEP, E_TOO_LONG, E_TRUNCATED, F_EOF, F_FRONT16, F_HIST,
+                   F_INDEX, F_INFER_START, F_LINE_START, OK)
 
 
 class FastqError(ValueError):
@@ -39,6 +39,7 @@ class Outcome:
     n_lines: int
     err_offset: int
     tail_offset: int | None
+    line_phase: int = 0
 
     def raise_for_status(self):
         if self.status != OK:
@@ -108,7 +109,7 @@ class Engine:
     def parse_device(self, d_bytes, n_own: int | None = None, n_avail: int | None = None, *,
                      hist: bool = True, index=None, line_base: int = 0, stream_offset: int = 0,
                      line_start: bool = True, eof: bool = True, front16: bool = False,
-                     stream=None) -> None:
+                     infer_start: bool = False, stream=None) -> None:
         """Enqueue delimit (+index) (+histograms) over a uint8 CUDA tensor (asynchronous).
         `d_bytes` may be a tensor or a raw device address."""
         ptr = d_bytes if isinstance(d_bytes, int) else d_bytes.data_ptr()
@@ -119,6 +120,7 @@ class Engine:
             n_own = n_avail
         flags = (F_HIST if hist else 0) | (F_INDEX if index is not None else 0)
         flags |= (F_LINE_START if line_start else 0) | (F_EOF if eof else 0) | (F_FRONT16 if front16 else 0)
+        flags |= F_INFER_START if infer_start else 0
         sh = _lib.Shard(ptr, n_own, n_avail, stream_offset, line_base, flags, 0,
                         index.data_ptr() if index is not None else None,
                         index.numel() if index is not None else 0)
@@ -137,7 +139,7 @@ class Engine:
     def _outcome(res) -> Outcome:
         tail = None if res.tail_offset == _lib.NO_OFFSET else int(res.tail_offset)
         return Outcome(int(res.status), bool(res.finished), int(res.n_records), int(res.n_lines),
-                       int(res.err_offset), tail)
+                       int(res.err_offset), tail, int(res.line_phase))
 
     def device_stats(self):
         """The device-resident stats block of the last parse as an int64 CUDA tensor view

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FQB_ABI_VERSION 1u
+#define FQB_ABI_VERSION 2u
 
 /* ---- status codes --------------------------------------------------------------------
  * 1..5 are the reference's grammar errors; the host shim maps each to
@@ -34,6 +34,8 @@ enum {
     FQB_E_TOO_LONG = 4,  /* "Fastq record is too long"                 src/lib.rs:278-283     */
     FQB_E_TRUNCATED = 5, /* "Possibly truncated input file"            src/lib.rs:286-291     */
     FQB_E_IO = 6,        /* reader error passed through                src/buffer.rs:86-96    */
+    FQB_E_PHASE = 7,     /* FQB_F_INFER_START: the first record of the shard could not be inferred
+                            from its bytes; parse again with the exact line_base              */
     FQB_E_ARG = 50,      /* bad argument (null pointer, misaligned buffer, ...) */
     FQB_E_STATE = 51,    /* call out of order (e.g. submit without acquire) */
     FQB_E_NOMEM = 52,
@@ -53,6 +55,13 @@ enum {
 #define FQB_F_FRONT16     0x10u /* d_bytes[-16..0) is readable and holds the 16 stream bytes
                                    before the shard (lets the kernel see whether the shard
                                    starts right after a '\n'); excludes FQB_F_LINE_START    */
+#define FQB_F_INFER_START 0x20u /* line_base is not known yet (a later shard of a multi-GPU job):
+                                   infer where the first record of the shard starts from the
+                                   grammar of the following records; fqb_result.line_phase reports
+                                   the line_base mod 4 that start implies.  The caller checks it
+                                   against the exact prefix of the shards' n_lines (which does not
+                                   depend on the phase) and parses again with the exact line_base
+                                   on a mismatch or on FQB_E_PHASE.                             */
 
 typedef struct fqb_ctx fqb_ctx;
 
@@ -97,6 +106,9 @@ typedef struct {
     uint64_t tail_offset;  /* stream offset of the first owned record that is incomplete within
                               n_avail without being an error (only without FQB_F_EOF);
                               UINT64_MAX if none */
+    uint32_t line_phase;   /* line_base mod 4 implied by where the first record of the shard was
+                              found (== line_base & 3 unless FQB_F_INFER_START) */
+    uint32_t reserved;
 } fqb_result;
 
 /* Statistics block: a flat array of uint64_t, fqb_stats_words(P) long, laid out

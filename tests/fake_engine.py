@@ -1,0 +1,103 @@
+"""CPU stand-in for fastq_rs_b200.Engine, for testing the N-rank driver (sharded.py) without a GPU.
+TEST INFRASTRUCTURE: it answers from the CPU oracle; it is never used by the product."""
+import numpy as np
+import torch
+
+from fastq_rs_b200.engine import Outcome
+from oracle import oracle
+
+E_PHASE = 7
+
+
+def stats_words(max_len, st, n_records):
+    """oracle Stats -> flat u64 block in the layout of include/fastq_b200.h"""
+    P = max_len
+    w = np.zeros(8 + P + 2 + 6 * P + 256 * P, dtype=np.uint64)
+    w[0], w[1] = n_records, st.n_bases
+    w[8:8 + P + 2] = st.len_hist
+    w[8 + P + 2:8 + P + 2 + 6 * P] = st.base_hist.reshape(-1)
+    w[8 + P + 2 + 6 * P:] = st.qual_hist.reshape(-1)
+    return w
+
+
+class FakeEngine:
+    def __init__(self, max_len=150, lie_phase=False, fail_infer=False):
+        self.max_len = max_len
+        self.lie_phase = lie_phase      # report a wrong inferred phase (the driver must parse again)
+        self.fail_infer = fail_infer    # answer E_PHASE to every inference
+        self.n_parses = 0
+        self._stats = torch.zeros(8 + max_len + 2 + 6 * max_len + 256 * max_len, dtype=torch.int64)
+        self._out = None
+
+    def count_lines(self, view, n):
+        return int((view[:n].numpy() == 10).sum())
+
+    def device_stats(self):
+        return self._stats
+
+    def fetch(self, want_stats=False):
+        return self._out, None
+
+    def parse_device(self, view, n_own, n_avail, hist=True, index=None, line_base=0, stream_offset=0,
+                     line_start=True, eof=True, front16=False, infer_start=False, stream=None):
+        self.n_parses += 1
+        self._stats.zero_()
+        buf = view[:n_avail].numpy()
+        n_lines = int((buf[:n_own] == 10).sum())
+        at_ls = line_start or (front16 and int(view.storage_offset()) >= 1 and
+                               int(view._base[view.storage_offset() - 1] if view._base is not None else 0) == 10)
+        nl = np.nonzero(buf == 10)[0]
+
+        def start_for(K):   # first record start when K owned newlines lie in front of it
+            if K == 0:
+                return 0
+            return int(nl[K - 1]) + 1 if K <= nl.size else None
+
+        def try_parse(start):
+            """records starting in [start, n_own): (status, err_offset, n_rec, end) via the oracle"""
+            res, recs = oracle.each(buf[start:].tobytes())
+            n, end = 0, start
+            for r in recs:
+                if start + r.offset >= n_own:
+                    break
+                n += 1
+                end = start + r.offset + len(r.raw)
+            status = 0
+            err = 0
+            if res.status != 0 and (len(recs) == n):   # the bad record is the next one
+                nxt = end
+                if nxt < n_own and not (not eof and res.status == 5 and False):
+                    status, err = res.status, stream_offset + nxt
+            return status, err, n, end
+
+        if infer_start:
+            if self.fail_infer:
+                self._out = Outcome(E_PHASE, False, 0, 0, 0, None, 0)
+                return
+            good = []
+            for K in ([0, 1, 2, 3] if at_ls else [1, 2, 3, 4]):
+                s = start_for(K)
+                if s is None:
+                    continue
+                st, _, n, _ = try_parse(s)
+                if st == 0 and n >= 2:
+                    good.append(K)
+            if len(good) != 1:
+                self._out = Outcome(E_PHASE, False, 0, 0, 0, None, 0)
+                return
+            K = good[0]
+            phase = (4 - K) & 3
+            if self.lie_phase:
+                phase = (phase + 1) & 3
+        else:
+            ph = line_base & 3
+            K = 0 if (at_ls and ph == 0) else 4 - ph
+            phase = ph
+        s = start_for(K)
+        if s is None:
+            s = n_avail
+        status, err, n_rec, end = try_parse(s)
+        if n_rec:
+            _, st = oracle.each_stats(buf[s:end].tobytes(), self.max_len)
+            self._stats[:] = torch.from_numpy(stats_words(self.max_len, st, n_rec).view(np.int64))
+        self._out = Outcome(status, status == 0, n_rec, n_lines, err, None, phase)

@@ -399,6 +399,62 @@ def test_shards_synthetic_unaligned_cuts(torch, oracle, eng):
     np.testing.assert_array_equal(total, _oracle_words(eng, ost))
 
 
+def test_shards_inferred_start(torch, oracle, eng):
+    """FQB_F_INFER_START: shards parsed without knowing the lines in front of them report the line
+    phase their first record implies; it must equal the true one, and the results the oracle's."""
+    n = 321 * 9000
+    data = oracle.synth_fixed(n, 150, 0).tobytes()
+    _, ost = oracle.each_stats(data, eng.max_len)
+    cuts = [0, 700001, 2889 * 321, 1500016, 2200333, n]      # mid-header, record start, mid-sequence, mid-quality
+    total = np.zeros_like(_oracle_words(eng, ost))
+    nrec = 0
+    full = to_dev(torch, data)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        buf = torch.zeros(16 + (n - a) + 64, dtype=torch.uint8, device="cuda")
+        lo = max(0, a - 16)
+        buf[16 - (a - lo):16 + (n - a)] = full[lo:n]
+        halo = min(n - b, 68 * 1024)
+        true_base = data[:a].count(b"\n")
+        # without the 16 bytes in front a shard cannot know that it starts a line: it then treats its
+        # first line as the tail of a line of the previous shard (the documented contract), which only
+        # matters for a cut exactly at a line start -- the phase and the newline count hold either way
+        for front in ([False] if a == 0 else [False, True]):
+            eng.parse_device(buf[16:], n_own=b - a, n_avail=b - a + halo, line_base=0, stream_offset=a,
+                             line_start=(a == 0), front16=(front and a > 0), eof=(b + halo == n),
+                             infer_start=(a > 0))
+            o, s = eng.fetch()
+            assert o.status == 0, (a, o)
+            assert o.line_phase == (true_base & 3), (a, front, o)
+            assert o.n_lines == data[a:b].count(b"\n")
+        nrec += o.n_records
+        total += s.words
+    assert nrec == ost.n_records
+    np.testing.assert_array_equal(total, _oracle_words(eng, ost))
+
+
+def test_inferred_start_ambiguous_is_reported(torch, fq, eng):
+    """A shard whose first record cannot be inferred (here: bytes that never form two records)
+    answers FQB_E_PHASE instead of guessing."""
+    data = b"ACGT" * 5000
+    t = to_dev(torch, data)
+    eng.parse_device(t, n_own=len(data), n_avail=len(data), line_start=False, eof=True, infer_start=True)
+    o, _ = eng.fetch()
+    assert o.status == fq._lib.E_PHASE
+
+
+def test_sharded_driver_single_rank(torch, fq, oracle, eng):
+    """sharded.py with the real engine, world = 1 (the N-rank protocol itself runs under gloo in
+    tests/test_sharded.py and on 2 GPUs in bench.py --gpus 2)."""
+    from fastq_rs_b200.sharded import ShardedParser, ShardSpec
+    data = oracle.synth_fixed(321 * 5000, 150, 0).tobytes()
+    _, ost = oracle.each_stats(data, eng.max_len)
+    t = to_dev(torch, data)
+    sp = ShardedParser(eng, dist=None, device="cuda")
+    out, st = sp.parse(ShardSpec(t, 0, len(data), 0, 0, True))
+    assert (out.status, out.n_records) == (0, 5000)
+    np.testing.assert_array_equal(st.words, _oracle_words(eng, ost))
+
+
 # --------------------------------------------------------------------------------------------
 # streaming ring: chunk boundaries, short fills, errors in later chunks
 # --------------------------------------------------------------------------------------------
