@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(so_path):
     for name in header_functions():
         assert hasattr(L, name), name
     L.fqb_abi_version.restype = C.c_uint32
-    assert L.fqb_abi_version() == 1
+    assert L.fqb_abi_version() == 2
 
 
 def test_no_torch_types_in_signatures():
