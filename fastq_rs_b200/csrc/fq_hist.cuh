@@ -83,6 +83,10 @@ __device__ void flush_hist(uint32_t* hist, const ScanParams& p, int first, int l
         const uint32_t chunk = (uint32_t)i / C::CHUNK_WORDS, r = (uint32_t)i % C::CHUNK_WORDS;
         const uint32_t b = r >> 5, pos = chunk * 32u + (r & 31u);
         const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+        // a '\n' counted INSIDE a sequence or quality line: the lines were not what the (predicting)
+        // delimiter took them for -- the exact path redoes the shard.  (Lines delimited by a scan end
+        // at their first '\n', so this row stays empty there.)
+        if (b == '\n') atomicExch(&p.res->spec_fail, 1);
         if (pos < P) {
             if (lo) atomicAdd(p.seqraw + (size_t)pos * 256 + b, (unsigned long long)lo);
             if (hi) atomicAdd(qual + (size_t)pos * 256 + b, (unsigned long long)hi);

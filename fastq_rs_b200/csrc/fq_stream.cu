@@ -250,11 +250,30 @@ struct SRounds<C, C::NCHUNK> {
     }
 };
 
-// returns true if a record of the pass failed validation
-template <class C>
-__device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s, const uint16_t* list,
-                                            const LaneK& lc, uint32_t hist_s, uint32_t* lenh, uint32_t Pm,
-                                            uint32_t n_rec, uint32_t pass, WinAcc& wa, int lane)
+// bytes [from, to) of the window (to - from <= 32) hold no '\n': lane i of the 8-lane group looks at
+// the 4 bytes from + 4i .. (two aligned words, funnel shift); lane-local answer, the caller votes
+__device__ __forceinline__ bool no_newline32(uint32_t buf_s, uint32_t from, uint32_t to, uint32_t i, uint32_t kA, uint32_t kB)
+{
+    const uint32_t a = buf_s + from + 4u * i;
+    const uint32_t w0 = lds32<0>(a & ~3u), w1 = lds32<4>(a & ~3u);
+    const uint32_t v = __funnelshift_r(w0, w1, a << 3);
+    const int left = (int)to - (int)(from + 4u * i);                      // bytes of the range in this lane's word
+    const uint32_t m = left >= 4 ? 0xFFFFFFFFu : (left > 0 ? ((1u << (8 * left)) - 1u) : 0u);
+    return (nlbits3(v, kA, kB) & m) == 0u;
+}
+
+// One pass over 4 records.  Returns the window-relative number of the first record of the pass that
+// did not hold (NO_START if all did).
+//   PRED = false: the list comes from the scan; a record that fails validation is an error.
+//   PRED = true : the list was PREDICTED from the shape of an earlier record; a record holds if its
+//                 four predicted line ends are '\n', its header and separator lines hold no other
+//                 '\n' and the usual validation passes.  (That its sequence and quality lines hold no
+//                 '\n' is checked by the histogram itself: row '\n' must stay empty, see flush_hist.)
+//                 Records from the first one that does not hold on are left to the next window.
+template <class C, bool PRED>
+__device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s,
+                                                const uint16_t* list, const LaneK& lc, uint32_t hist_s, uint32_t* lenh,
+                                                uint32_t Pm, uint32_t n_rec, uint32_t pass, WinAcc& wa, int lane)
 {
     const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
     const uint32_t r = 4u * pass + sub;
@@ -265,7 +284,26 @@ __device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* 
     const uint32_t c_at = buf[s], c_plus = buf[q + 1], c_sr = buf[q - 1], c_qr = buf[e - 1];
     // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
     const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
-    const bool ok = valid && good;
+    bool ok = valid && good;
+    uint32_t first_bad = NO_START;
+    if (PRED) {
+        const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
+        // lanes 0..3: the predicted line ends; all lanes: no other '\n' in the header (<= 64 bytes) and
+        // in the separator line behind its '+' (<= 32 bytes)
+        bool lane_ok = i >= 4u || buf[(uint32_t)lp[i + 1u] - 1u] == '\n';
+        lane_ok = lane_ok && no_newline32(buf_s, s, min(h, s + 32u), i, kA, kB);
+        if (h > s + 32u) lane_ok = lane_ok && no_newline32(buf_s, s + 32u, h, i, kA, kB);
+        if (pp > q + 2u) lane_ok = lane_ok && no_newline32(buf_s, q + 2u, pp, i, kA, kB);
+        const unsigned nok = __ballot_sync(0xffffffffu, valid && !(good && lane_ok));
+        if (nok) {
+            const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;     // first group with a lane that objects
+            first_bad = 4u * pass + fsub;
+            ok = valid && sub < fsub;
+        }
+    } else {
+        const unsigned nok = __ballot_sync(0xffffffffu, valid && !good);
+        if (nok) first_bad = 4u * pass + (((uint32_t)__ffs(nok) - 1u) >> 3);
+    }
     if (p.flags & F_HIST) {
         uint32_t Ls = 0, Lq = 0;
         if (ok) {
@@ -304,7 +342,34 @@ __device__ __forceinline__ bool stream_pass(const ScanParams& p, const uint8_t* 
     } else if (ok && i == 0) {
         wa.n_records++;
     }
-    return __any_sync(0xffffffffu, valid && !good);
+    return first_bad;
+}
+
+// line starts of a window PREDICTED from the shape of an earlier record: record r starts at
+// pad + r * reclen, its lines are Lh, Lsq, Lp, Lsq bytes long (each with its '\n')
+__device__ __forceinline__ void fill_list(uint16_t* list, uint32_t pad, uint32_t n, uint32_t Lh, uint32_t Lsq, uint32_t Lp,
+                                          int lane)
+{
+    const uint32_t reclen = Lh + 2u * Lsq + Lp;
+    for (uint32_t j = lane; j <= 4u * n; j += 32) {
+        const uint32_t rec = j >> 2, k = j & 3u;
+        const uint32_t off = k == 0 ? 0u : (k == 1 ? Lh : (k == 2 ? Lh + Lsq : Lh + Lsq + Lp));
+        list[j] = (uint16_t)(pad + rec * reclen + off);
+    }
+    __syncwarp();
+}
+
+// OR of all words of the window (bytes >= 0x80 must not reach the dp4a addressing of the rounds)
+template <class C>
+__device__ __forceinline__ bool win_has_high_bytes(const uint8_t* buf, int lane)
+{
+    uint32_t hib = 0;
+#pragma unroll
+    for (int it = 0; it < C::NU; ++it) {
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + it * UNIT + lane * 16);
+        hib |= v.x | v.y | v.z | v.w;
+    }
+    return __any_sync(0xffffffffu, (hib & 0x80808080u) != 0);
 }
 
 struct StreamCta {
@@ -420,14 +485,34 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
 
         // ---- stream through the range ------------------------------------------------------------
         const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
+        // shape of the last record delimited by a scan (line lengths with their '\n'): while it keeps
+        // predicting the following records, windows are not scanned at all
+        uint32_t Lh = 0, Lsq = 0, Lp = 0;
+        bool predict = false;
+        uint32_t strikes = 0, cooldown = 0;
         while (!failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
-            uint32_t hib;
-            const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
-            const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
-            if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
-                failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
-                break;
+            uint32_t n_win = 0;
+            bool predicted = false;
+            if (predict && w.vlen == (uint32_t)C::WIN) {
+                n_win = min((w.vlen - w.pad) / (Lh + 2u * Lsq + Lp), (uint32_t)C::MAXR);
+                if (n_win) {
+                    if (win_has_high_bytes<C>(buf, lane)) {
+                        failed = true;   // bytes >= 0x80: the exact path
+                        break;
+                    }
+                    fill_list(list, w.pad, n_win, Lh, Lsq, Lp, lane);
+                    predicted = true;
+                }
+            }
+            if (!predicted) {
+                uint32_t hib;
+                const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
+                n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
+                if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                    failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
+                    break;
+                }
             }
             // records of the window that start inside the range (their starts increase); everything
             // below is relative to the window
@@ -439,13 +524,35 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                 const bool vb = rb < n_win && list[4u * min(rb, (uint32_t)C::MAXR)] < (uint32_t)room;
                 n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
             }
-            bool bad = false;
             WinAcc wa = {0, 0};
-            for (uint32_t pass = 0; 4u * pass < n_rec; ++pass)
-                bad |= stream_pass<C>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
-            if (bad) {
-                failed = true;   // a record that fails validation: the exact path finds and classifies it
-                break;
+            if (predicted) {
+                uint32_t first_bad = NO_START;
+                for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
+                    first_bad = stream_pass<C, true>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
+                if (first_bad != NO_START) {
+                    // the prediction stops holding at this record: consume what came before it, scan next time
+                    n_rec = first_bad;
+                    predict = false;
+                    if (first_bad == 0 && ++strikes >= 2) cooldown = 32;   // (variable-length reads: stop trying for a while)
+                } else {
+                    strikes = 0;
+                }
+                if (n_rec == 0) continue;
+            } else {
+                uint32_t first_bad = NO_START;
+                for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
+                    first_bad = stream_pass<C, false>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
+                if (first_bad != NO_START) {
+                    failed = true;   // a record that fails validation: the exact path finds and classifies it
+                    break;
+                }
+                // the shape the next windows are predicted with (only while the histogram checks the
+                // sequence and quality lines for stray '\n': every byte of them must have a counter)
+                Lh = (uint32_t)list[1] - list[0];
+                Lsq = (uint32_t)list[2] - list[1];
+                Lp = (uint32_t)list[3] - list[2];
+                if (cooldown) --cooldown;
+                predict = (p.flags & F_HIST) && cooldown == 0 && Lsq - 1u <= Pm && Lh <= 64u && Lp <= 34u;
             }
             {
                 const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
@@ -483,7 +590,6 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                 my_epoch = ep;
                 flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
             }
-            if (n_rec < n_win) break;                             // the next record belongs to the next range
         }
         // data that ends inside the owned bytes without a record boundary: not a clean shard
         if (!failed && cur < R1) failed = true;
