@@ -64,9 +64,29 @@ __device__ __forceinline__ uint32_t nlmask16k(const uint4& v, uint32_t kA, uint3
     return lo + (hi << 8);
 }
 
+// shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loops)
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 
 struct Window {
@@ -110,19 +130,19 @@ __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, un
 // sends the unit through the generic path.  Returns the newline count; hib = OR of all words.
 // RAGGED: the window is shorter than WIN (the end of the shard) -- stale bytes are masked out.
 template <class C, bool RAGGED>
-__device__ __forceinline__ uint32_t win_scan_t(const uint8_t* buf, uint16_t* list, const Window& w, uint32_t& hib,
+__device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib,
                                                int lane, uint32_t lt_mask)
 {
     const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
-    if (lane == 0) list[0] = (uint16_t)w.pad;
+    const uint32_t list_s = buf_s + (uint32_t)(C::WIN + 16);
+    if (lane == 0) sts16(list_s, w.pad);
     uint32_t ubase = 1;
     hib = 0;
-    const uint32_t list_s = smem_u32(list);
     const uint32_t lane_pos = (uint32_t)lane * 16u - 7u + 1u;              // bit index -> position + 1
 #pragma unroll
     for (int it = 0; it < C::NU; ++it) {
         const uint32_t off = (uint32_t)it * UNIT + (uint32_t)lane * 16u;
-        const uint4 v = *reinterpret_cast<const uint4*>(buf + off);
+        const uint4 v = lds_v4(buf_s + off);
         hib |= v.x | v.y | v.z | v.w;
         uint32_t mm = nlmask16k(v, kA, kB);                                 // bit 7 + i = byte i of the piece
         if (it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
@@ -159,11 +179,11 @@ __device__ __forceinline__ uint32_t win_scan_t(const uint8_t* buf, uint16_t* lis
 }
 
 template <class C>
-__device__ __forceinline__ uint32_t win_scan(const uint8_t* buf, uint16_t* list, const Window& w, uint32_t& hib,
+__device__ __forceinline__ uint32_t win_scan(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib,
                                              int lane, uint32_t lt_mask)
 {
-    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true>(buf, list, w, hib, lane, lt_mask);
-    return win_scan_t<C, false>(buf, list, w, hib, lane, lt_mask);
+    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true>(buf_s, list, w, hib, lane, lt_mask);
+    return win_scan_t<C, false>(buf_s, list, w, hib, lane, lt_mask);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,16 +292,17 @@ __device__ __forceinline__ bool no_newline32(uint32_t buf_s, uint32_t from, uint
 //                 Records from the first one that does not hold on are left to the next window.
 template <class C, bool PRED>
 __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s,
-                                                const uint16_t* list, const LaneK& lc, uint32_t hist_s, uint32_t* lenh,
-                                                uint32_t Pm, uint32_t n_rec, uint32_t pass, WinAcc& wa, int lane)
+                                                const LaneK& lc, uint32_t hist_s, uint32_t* lenh, uint32_t Pm,
+                                                uint32_t n_rec, uint32_t pass, WinAcc& wa, uint32_t sub, uint32_t i)
 {
-    const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
     const uint32_t r = 4u * pass + sub;
     const bool valid = r < n_rec;
     // lanes without a record look at record 0 of the window (real data, harmless) and are masked out below
-    const uint16_t* lp = list + (valid ? 4u * r : 0u);
-    const uint32_t s = lp[0], h = lp[1] - 1u, q = lp[2] - 1u, pp = lp[3] - 1u, e = lp[4] - 1u;
-    const uint32_t c_at = buf[s], c_plus = buf[q + 1], c_sr = buf[q - 1], c_qr = buf[e - 1];
+    const uint32_t lp = buf_s + (uint32_t)(C::WIN + 16) + (valid ? 8u * r : 0u);
+    const uint32_t s = lds_u16<0>(lp), h = lds_u16<2>(lp) - 1u, q = lds_u16<4>(lp) - 1u, pp = lds_u16<6>(lp) - 1u,
+                   e = lds_u16<8>(lp) - 1u;
+    const uint32_t c_at = lds_u8(buf_s + s), c_plus = lds_u8(buf_s + q + 1u), c_sr = lds_u8(buf_s + q - 1u),
+                   c_qr = lds_u8(buf_s + e - 1u);
     // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
     const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
     bool ok = valid && good;
@@ -290,7 +311,7 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
         // lanes 0..3: the predicted line ends; all lanes: no other '\n' in the header (<= 64 bytes) and
         // in the separator line behind its '+' (<= 32 bytes)
-        bool lane_ok = i >= 4u || buf[(uint32_t)lp[i + 1u] - 1u] == '\n';
+        bool lane_ok = i >= 4u || lds_u8(buf_s + lds_u16<2>(lp + 2u * i) - 1u) == '\n';
         lane_ok = lane_ok && no_newline32(buf_s, s, min(h, s + 32u), i, kA, kB);
         if (h > s + 32u) lane_ok = lane_ok && no_newline32(buf_s, s + 32u, h, i, kA, kB);
         if (pp > q + 2u) lane_ok = lane_ok && no_newline32(buf_s, q + 2u, pp, i, kA, kB);
@@ -347,26 +368,26 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
 
 // line starts of a window PREDICTED from the shape of an earlier record: record r starts at
 // pad + r * reclen, its lines are Lh, Lsq, Lp, Lsq bytes long (each with its '\n')
-__device__ __forceinline__ void fill_list(uint16_t* list, uint32_t pad, uint32_t n, uint32_t Lh, uint32_t Lsq, uint32_t Lp,
+__device__ __forceinline__ void fill_list(uint32_t list_s, uint32_t pad, uint32_t n, uint32_t Lh, uint32_t Lsq, uint32_t Lp,
                                           int lane)
 {
     const uint32_t reclen = Lh + 2u * Lsq + Lp;
-    for (uint32_t j = lane; j <= 4u * n; j += 32) {
-        const uint32_t rec = j >> 2, k = j & 3u;
-        const uint32_t off = k == 0 ? 0u : (k == 1 ? Lh : (k == 2 ? Lh + Lsq : Lh + Lsq + Lp));
-        list[j] = (uint16_t)(pad + rec * reclen + off);
-    }
+    // lane = 4 * (record mod 8) + line: the line offset is fixed per lane, a step is 8 records
+    const uint32_t k = (uint32_t)lane & 3u;
+    const uint32_t off = k == 0 ? 0u : (k == 1 ? Lh : (k == 2 ? Lh + Lsq : Lh + Lsq + Lp));
+    uint32_t v = pad + ((uint32_t)lane >> 2) * reclen + off;
+    for (uint32_t j = lane; j <= 4u * n; j += 32, v += 8u * reclen) sts16(list_s + 2u * j, v);
     __syncwarp();
 }
 
 // OR of all words of the window (bytes >= 0x80 must not reach the dp4a addressing of the rounds)
 template <class C>
-__device__ __forceinline__ bool win_has_high_bytes(const uint8_t* buf, int lane)
+__device__ __forceinline__ bool win_has_high_bytes(uint32_t buf_s, int lane)
 {
     uint32_t hib = 0;
 #pragma unroll
     for (int it = 0; it < C::NU; ++it) {
-        const uint4 v = *reinterpret_cast<const uint4*>(buf + it * UNIT + lane * 16);
+        const uint4 v = lds_v4(buf_s + (uint32_t)(it * UNIT + lane * 16));
         hib |= v.x | v.y | v.z | v.w;
     }
     return __any_sync(0xffffffffu, (hib & 0x80808080u) != 0);
@@ -414,9 +435,11 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     uint32_t parity = 0;
 
     const uint32_t hist_s = smem_u32(hist);
+    uint32_t sub = (uint32_t)lane >> 3, li = (uint32_t)lane & 7u;
+    asm volatile("" : "+r"(sub), "+r"(li));
     LaneK lc;
     {
-        const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
+        const uint32_t i = li;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
@@ -448,7 +471,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             const bool front = rid != 0 || (p.flags & F_FRONT16);
             const Window w = win_load<C>(p, buf, bar, parity, (long long)R0 - (front ? 1 : 0), lane);
             uint32_t hib;
-            const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
+            const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
             const uint32_t nstored = min(total, (uint32_t)C::LIST_N - 2u);
             const uint32_t neg = (front && nstored >= 1u && list[1] == 16u) ? 1u : 0u;   // a '\n' right in front of the range
             uint32_t c;
@@ -497,17 +520,17 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             if (predict && w.vlen == (uint32_t)C::WIN) {
                 n_win = min((w.vlen - w.pad) / (Lh + 2u * Lsq + Lp), (uint32_t)C::MAXR);
                 if (n_win) {
-                    if (win_has_high_bytes<C>(buf, lane)) {
+                    if (win_has_high_bytes<C>(buf_s, lane)) {
                         failed = true;   // bytes >= 0x80: the exact path
                         break;
                     }
-                    fill_list(list, w.pad, n_win, Lh, Lsq, Lp, lane);
+                    fill_list(buf_s + (uint32_t)(C::WIN + 16), w.pad, n_win, Lh, Lsq, Lp, lane);
                     predicted = true;
                 }
             }
             if (!predicted) {
                 uint32_t hib;
-                const uint32_t total = win_scan<C>(buf, list, w, hib, lane, lt_mask);
+                const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
                 n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
                 if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
@@ -528,7 +551,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             if (predicted) {
                 uint32_t first_bad = NO_START;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = stream_pass<C, true>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
+                    first_bad = stream_pass<C, true>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
                     // the prediction stops holding at this record: consume what came before it, scan next time
                     n_rec = first_bad;
@@ -541,7 +564,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
             } else {
                 uint32_t first_bad = NO_START;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = stream_pass<C, false>(p, buf, buf_s, list, lc, hist_s, lenh, Pm, n_rec, pass, wa, lane);
+                    first_bad = stream_pass<C, false>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
                     failed = true;   // a record that fails validation: the exact path finds and classifies it
                     break;
@@ -575,7 +598,8 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                 }
                 const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;   // low 32 bits are what the index holds
                 uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
-                for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + list[j + 1u];
+                const uint32_t ls = buf_s + (uint32_t)(C::WIN + 16) + 2u;
+                for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + lds_u16<0>(ls + 2u * j);
             }
             lrank += n_lines;
             cur = w.src + next;
