@@ -282,15 +282,9 @@ __device__ __forceinline__ bool no_newline32(uint32_t buf_s, uint32_t from, uint
     return (nlbits3(v, kA, kB) & m) == 0u;
 }
 
-// One pass over 4 records.  Returns the window-relative number of the first record of the pass that
-// did not hold (NO_START if all did).
-//   PRED = false: the list comes from the scan; a record that fails validation is an error.
-//   PRED = true : the list was PREDICTED from the shape of an earlier record; a record holds if its
-//                 four predicted line ends are '\n', its header and separator lines hold no other
-//                 '\n' and the usual validation passes.  (That its sequence and quality lines hold no
-//                 '\n' is checked by the histogram itself: row '\n' must stay empty, see flush_hist.)
-//                 Records from the first one that does not hold on are left to the next window.
-template <class C, bool PRED>
+// One pass over 4 records whose line starts come from the scan's list.  Returns the window-relative
+// number of the first record of the pass that failed validation (NO_START if none did).
+template <class C>
 __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s,
                                                 const LaneK& lc, uint32_t hist_s, uint32_t* lenh, uint32_t Pm,
                                                 uint32_t n_rec, uint32_t pass, WinAcc& wa, uint32_t sub, uint32_t i)
@@ -305,23 +299,9 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
                    c_qr = lds_u8(buf_s + e - 1u);
     // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
     const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
-    bool ok = valid && good;
+    const bool ok = valid && good;
     uint32_t first_bad = NO_START;
-    if (PRED) {
-        const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
-        // lanes 0..3: the predicted line ends; all lanes: no other '\n' in the header (<= 64 bytes) and
-        // in the separator line behind its '+' (<= 32 bytes)
-        bool lane_ok = i >= 4u || lds_u8(buf_s + lds_u16<2>(lp + 2u * i) - 1u) == '\n';
-        lane_ok = lane_ok && no_newline32(buf_s, s, min(h, s + 32u), i, kA, kB);
-        if (h > s + 32u) lane_ok = lane_ok && no_newline32(buf_s, s + 32u, h, i, kA, kB);
-        if (pp > q + 2u) lane_ok = lane_ok && no_newline32(buf_s, q + 2u, pp, i, kA, kB);
-        const unsigned nok = __ballot_sync(0xffffffffu, valid && !(good && lane_ok));
-        if (nok) {
-            const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;     // first group with a lane that objects
-            first_bad = 4u * pass + fsub;
-            ok = valid && sub < fsub;
-        }
-    } else {
+    {
         const unsigned nok = __ballot_sync(0xffffffffu, valid && !good);
         if (nok) first_bad = 4u * pass + (((uint32_t)__ffs(nok) - 1u) >> 3);
     }
@@ -366,18 +346,51 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
     return first_bad;
 }
 
-// line starts of a window PREDICTED from the shape of an earlier record: record r starts at
-// pad + r * reclen, its lines are Lh, Lsq, Lp, Lsq bytes long (each with its '\n')
-__device__ __forceinline__ void fill_list(uint32_t list_s, uint32_t pad, uint32_t n, uint32_t Lh, uint32_t Lsq, uint32_t Lp,
-                                          int lane)
+// ------------------------------------------------------------------------------------------
+// PREDICTED windows.  While the records keep the shape of the last record a scan delimited (line
+// lengths Lh, Lsq, Lp, Lsq with their '\n'; '\r' before the '\n' of the sequence / quality line or
+// not), a window is not scanned at all: record r starts at pad + r * reclen and is VERIFIED instead:
+//   lane i of its 8 lanes checks one byte: '@', the four '\n', '+', and the two bytes that decide
+//   the '\r' trimming; all lanes check that header and separator line hold no other '\n';
+//   that the sequence and quality lines hold no '\n' is checked by the histogram itself -- every
+//   byte of them is counted (Lsq - 1 <= positions with a counter), and a count in row '\n' raises
+//   spec_fail when the counters are drained (flush_hist).
+// A record that does not verify ends the prediction: it and everything behind it is left to the
+// next window, which scans.  Per record this costs ~1/4 of the scan and no list.
+// ------------------------------------------------------------------------------------------
+struct Shape {
+    uint32_t Lh, Lsq, Lp;     // header / sequence (= quality) / separator line length, each with its '\n'
+    uint32_t cr_s, cr_q;      // 1 if the byte before the '\n' of the sequence / quality line is '\r'
+    uint32_t reclen;
+};
+
+template <class C>
+__device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, uint32_t pad, uint32_t chk_off,
+                                              uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t nq,
+                                              const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
+                                              uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB)
 {
-    const uint32_t reclen = Lh + 2u * Lsq + Lp;
-    // lane = 4 * (record mod 8) + line: the line offset is fixed per lane, a step is 8 records
-    const uint32_t k = (uint32_t)lane & 3u;
-    const uint32_t off = k == 0 ? 0u : (k == 1 ? Lh : (k == 2 ? Lh + Lsq : Lh + Lsq + Lp));
-    uint32_t v = pad + ((uint32_t)lane >> 2) * reclen + off;
-    for (uint32_t j = lane; j <= 4u * n; j += 32, v += 8u * reclen) sts16(list_s + 2u * j, v);
-    __syncwarp();
+    const uint32_t r = 4u * pass + sub;
+    const bool valid = r < n_rec;
+    const uint32_t s = buf_s + pad + (valid ? r : 0u) * sh.reclen;        // shared address of the record
+    bool lane_ok = ((lds_u8(s + chk_off) == chk_exp) ? 1u : 0u) != chk_neg;
+    lane_ok = lane_ok && no_newline32(s, 0u, min(sh.Lh - 1u, 32u), i, kA, kB);
+    if (sh.Lh > 33u) lane_ok = lane_ok && no_newline32(s, 32u, sh.Lh - 1u, i, kA, kB);
+    if (sh.Lp > 2u) lane_ok = lane_ok && no_newline32(s, sh.Lh + sh.Lsq + 1u, sh.Lh + sh.Lsq + sh.Lp - 1u, i, kA, kB);
+    const unsigned nok = __ballot_sync(0xffffffffu, valid && !lane_ok);
+    uint32_t first_bad = NO_START;
+    bool ok = valid;
+    if (nok) {
+        const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;             // first group with a lane that objects
+        first_bad = 4u * pass + fsub;
+        ok = valid && sub < fsub;
+    }
+    const uint32_t sa = s + sh.Lh + 4u * i;                    // position 4i of the sequence line
+    const uint32_t qa = sa + sh.Lsq + sh.Lp;                   // ... of the quality line
+    // lanes without a (holding) record do not hold the fast rounds back: their bumps add zero
+    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ok ? ns : 0u, ok ? nq : 0u, max(ns, nq), min(ns, nq),
+                       ok ? 1u : 0u, ok ? 0x10000u : 0u, hist_s, lc);
+    return first_bad;
 }
 
 // OR of all words of the window (bytes >= 0x80 must not reach the dp4a addressing of the rounds)
@@ -508,50 +521,38 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
 
         // ---- stream through the range ------------------------------------------------------------
         const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
-        // shape of the last record delimited by a scan (line lengths with their '\n'): while it keeps
-        // predicting the following records, windows are not scanned at all
-        uint32_t Lh = 0, Lsq = 0, Lp = 0;
+        // shape of the last record delimited by a scan: while it keeps predicting the following
+        // records, windows are not scanned at all (see pred_pass)
+        Shape sh = {0, 0, 0, 0, 0, 1};
         bool predict = false;
         uint32_t strikes = 0, cooldown = 0;
+        const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
         while (!failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
-            uint32_t n_win = 0;
-            bool predicted = false;
-            if (predict && w.vlen == (uint32_t)C::WIN) {
-                n_win = min((w.vlen - w.pad) / (Lh + 2u * Lsq + Lp), (uint32_t)C::MAXR);
-                if (n_win) {
-                    if (win_has_high_bytes<C>(buf_s, lane)) {
-                        failed = true;   // bytes >= 0x80: the exact path
-                        break;
-                    }
-                    fill_list(buf_s + (uint32_t)(C::WIN + 16), w.pad, n_win, Lh, Lsq, Lp, lane);
-                    predicted = true;
-                }
-            }
-            if (!predicted) {
-                uint32_t hib;
-                const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
-                n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
-                if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
-                    failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
+            const unsigned long long room = R1 - w.src;          // > pad: window bytes inside the range
+            uint32_t n_rec, n_lines, next;
+            // ---- predicted window: full, inside the owned bytes, at least one record ------------------
+            const uint32_t n_fit = (uint32_t)(C::WIN - w.pad) / sh.reclen;
+            if (predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own) {
+                if (win_has_high_bytes<C>(buf_s, lane)) {
+                    failed = true;   // bytes >= 0x80: the exact path
                     break;
                 }
-            }
-            // records of the window that start inside the range (their starts increase); everything
-            // below is relative to the window
-            uint32_t n_rec = n_win;
-            const unsigned long long room = R1 - w.src;          // > pad
-            if (room < (unsigned long long)C::WIN) {              // the range ends inside this window
-                const uint32_t ra = (uint32_t)lane, rb = (uint32_t)lane + 32u;
-                const bool va = ra < n_win && list[4u * ra] < (uint32_t)room;
-                const bool vb = rb < n_win && list[4u * min(rb, (uint32_t)C::MAXR)] < (uint32_t)room;
-                n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
-            }
-            WinAcc wa = {0, 0};
-            if (predicted) {
+                // records that start inside the range
+                n_rec = n_fit;
+                if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
+                // the byte every lane verifies per record (relative to the record start)
+                const uint32_t o2 = sh.Lh + sh.Lsq;
+                const uint32_t chk_off = li == 0 ? 0u : li == 1 ? sh.Lh - 1u : li == 2 ? o2 - 1u : li == 3 ? o2
+                                       : li == 4 ? o2 + sh.Lp - 1u : li == 5 ? sh.reclen - 1u : li == 6 ? o2 - 2u : sh.reclen - 2u;
+                const uint32_t chk_exp = li == 0 ? '@' : li == 3 ? '+' : li >= 6 ? '\r' : '\n';
+                const uint32_t chk_neg = (li == 6 && !sh.cr_s) || (li == 7 && !sh.cr_q) ? 1u : 0u;
+                const uint32_t Lr = sh.Lsq - 1u;
+                const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;       // seq()/qual() drop one trailing '\r'
                 uint32_t first_bad = NO_START;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = stream_pass<C, true>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
+                    first_bad = pred_pass<C>(buf_s, sh, w.pad, chk_off, chk_exp, chk_neg, Ls, Lq, lc, hist_s, n_rec, pass,
+                                             sub, li, kA, kB);
                 if (first_bad != NO_START) {
                     // the prediction stops holding at this record: consume what came before it, scan next time
                     n_rec = first_bad;
@@ -561,45 +562,88 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
                     strikes = 0;
                 }
                 if (n_rec == 0) continue;
+                if (lane == 0) {
+                    atomicAdd(&cta.n_records, n_rec);
+                    atomicAdd(&cta.n_bases, n_rec * Ls);
+                    atomicAdd(lenh + Ls, n_rec);
+                }
+                n_lines = 4u * n_rec;
+                next = w.pad + n_rec * sh.reclen;
+                if (want_index) {
+                    if (lrank + n_lines > p.stage_share) {
+                        failed = true;   // staging share too small: the exact path writes the index
+                        break;
+                    }
+                    // lane = 4 * (record mod 8) + line: the line-end offset is fixed per lane
+                    const uint32_t k = (uint32_t)lane & 3u;
+                    const uint32_t le = k == 0 ? sh.Lh - 1u : k == 1 ? o2 - 1u : k == 2 ? o2 + sh.Lp - 1u : sh.reclen - 1u;
+                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + le;
+                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
+                    for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
+                }
             } else {
+                // ---- scanned window -------------------------------------------------------------------
+                uint32_t hib;
+                const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
+                const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
+                if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                    failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
+                    break;
+                }
+                // records of the window that start inside the range (their starts increase)
+                n_rec = n_win;
+                if (room < (unsigned long long)C::WIN) {              // the range ends inside this window
+                    const uint32_t ra = (uint32_t)lane, rb = (uint32_t)lane + 32u;
+                    const bool va = ra < n_win && list[4u * ra] < (uint32_t)room;
+                    const bool vb = rb < n_win && list[4u * min(rb, (uint32_t)C::MAXR)] < (uint32_t)room;
+                    n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
+                }
+                WinAcc wa = {0, 0};
                 uint32_t first_bad = NO_START;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = stream_pass<C, false>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
+                    first_bad = stream_pass<C>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
                     failed = true;   // a record that fails validation: the exact path finds and classifies it
                     break;
                 }
-                // the shape the next windows are predicted with (only while the histogram checks the
-                // sequence and quality lines for stray '\n': every byte of them must have a counter)
-                Lh = (uint32_t)list[1] - list[0];
-                Lsq = (uint32_t)list[2] - list[1];
-                Lp = (uint32_t)list[3] - list[2];
-                if (cooldown) --cooldown;
-                predict = (p.flags & F_HIST) && cooldown == 0 && Lsq - 1u <= Pm && Lh <= 64u && Lp <= 34u;
-            }
-            {
-                const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
-                if (lane == 0) {
-                    atomicAdd(&cta.n_records, nr);
-                    atomicAdd(&cta.n_bases, nb);
+                {
+                    const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
+                    if (lane == 0) {
+                        atomicAdd(&cta.n_records, nr);
+                        atomicAdd(&cta.n_bases, nb);
+                    }
                 }
-            }
-            // line ends of the consumed records that lie in the owned bytes of the shard
-            uint32_t n_lines = 4u * n_rec;
-            const uint32_t next = list[n_lines];                  // start of the first record not consumed
-            if (w.src + next - 1u >= p.n_own) {                   // the shard's last record reaches beyond n_own
-                const bool in = lane < 4 && w.src + list[n_lines - 3u + (uint32_t)lane] - 1u < p.n_own;
-                n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
-            }
-            if (want_index) {
-                if (lrank + n_lines > p.stage_share) {
-                    failed = true;   // staging share too small: the exact path writes the index
-                    break;
+                // the shape the next windows are predicted with -- only while the histogram checks the
+                // sequence and quality lines for stray '\n': every byte of them must have a counter
+                {
+                    const uint32_t l0 = list[0], l1 = list[1], l2 = list[2], l3 = list[3], l4 = list[4];
+                    sh.Lh = l1 - l0;
+                    sh.Lsq = l2 - l1;
+                    sh.Lp = l3 - l2;
+                    sh.reclen = l4 - l0;
+                    sh.cr_s = (sh.Lsq > 1u && buf[l2 - 2u] == '\r') ? 1u : 0u;
+                    sh.cr_q = (sh.Lsq > 1u && buf[l4 - 2u] == '\r') ? 1u : 0u;
+                    if (cooldown) --cooldown;
+                    predict = (p.flags & F_HIST) && cooldown == 0 && sh.Lsq - 1u <= Pm && sh.Lh >= 2u && sh.Lh <= 64u &&
+                              sh.Lp >= 2u && sh.Lp <= 34u;
                 }
-                const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;   // low 32 bits are what the index holds
-                uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
-                const uint32_t ls = buf_s + (uint32_t)(C::WIN + 16) + 2u;
-                for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + lds_u16<0>(ls + 2u * j);
+                // line ends of the consumed records that lie in the owned bytes of the shard
+                n_lines = 4u * n_rec;
+                next = list[n_lines];                             // start of the first record not consumed
+                if (w.src + next - 1u >= p.n_own) {               // the shard's last record reaches beyond n_own
+                    const bool in = lane < 4 && w.src + list[n_lines - 3u + (uint32_t)lane] - 1u < p.n_own;
+                    n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
+                }
+                if (want_index) {
+                    if (lrank + n_lines > p.stage_share) {
+                        failed = true;   // staging share too small: the exact path writes the index
+                        break;
+                    }
+                    const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;   // low 32 bits are what the index holds
+                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
+                    const uint32_t ls = buf_s + (uint32_t)(C::WIN + 16) + 2u;
+                    for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + lds_u16<0>(ls + 2u * j);
+                }
             }
             lrank += n_lines;
             cur = w.src + next;
