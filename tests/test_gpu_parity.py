@@ -331,6 +331,67 @@ def test_error_mid_stream(kind, torch, oracle, eng):
 
 
 # --------------------------------------------------------------------------------------------
+# the predicting delimiter (fq_stream.cu: windows whose records keep the shape of the last scanned
+# record are verified instead of scanned): everything that must end or defeat a prediction
+# --------------------------------------------------------------------------------------------
+def _plain_rec(head: bytes, L: int, i: int, eol=b"\n"):
+    seq = bytes(b"ACGT"[(i * 7 + j * 3) & 3] for j in range(L))
+    qual = bytes(33 + ((i + j * 5) % 41) for j in range(L))
+    return b"@" + head + eol + seq + eol + b"+" + eol + qual + eol
+
+
+def test_prediction_header_length_changes(torch, oracle, eng):
+    # unpadded ids: the header grows by one byte at 10, 100, 1000, 10000 -- each time the prediction
+    # must stop exactly there and a scan take over
+    data = b"".join(_plain_rec(b"r%d" % i, 100, i) for i in range(12000))
+    check_device_vs_oracle(torch, oracle, eng, data)
+
+
+def test_prediction_alternating_lengths(torch, oracle, eng):
+    # read lengths that change every few records (trimmed reads): predictions fail all the time
+    data = b"".join(_plain_rec(b"x%05d" % i, 60 + 13 * ((i // 3) % 7), i) for i in range(9000))
+    check_device_vs_oracle(torch, oracle, eng, data)
+
+
+def test_prediction_crlf_and_mixed_endings(torch, oracle, eng):
+    # CRLF records keep their shape (prediction on), then a block of LF records, then records whose
+    # quality line alone carries the \r (raw lengths still equal? no: that is a length error) -> stop
+    a = b"".join(_plain_rec(b"c%06d" % i, 120, i, eol=b"\r\n") for i in range(3000))
+    b = b"".join(_plain_rec(b"l%06d" % i, 120, i) for i in range(3000))
+    check_device_vs_oracle(torch, oracle, eng, a + b + a)
+
+
+@pytest.mark.parametrize("where", ["seq", "qual", "header", "sep"])
+def test_prediction_stray_newline(where, torch, oracle, eng):
+    """A '\n' inside a line of a record deep inside a predicted run: all predicted line ends are
+    still '\n', so only the extra checks (header / separator scan, the empty '\n' row of the
+    histogram) can notice that the lines are not what the prediction takes them for."""
+    recs = [_plain_rec(b"id%07d+x" % i, 150, i) for i in range(6000)]
+    k = 4321
+    r = bytearray(recs[k])
+    hl = len(b"id%07d+x" % k) + 2
+    pos = {"header": 5, "seq": hl + 77, "sep": hl + 151, "qual": hl + 151 + 2 + 40}[where]
+    if where == "sep":
+        r = bytearray(recs[k].replace(b"\n+\n", b"\n+ab\n"))   # a separator line with text ...
+        recs = [x.replace(b"\n+\n", b"\n+ab\n") for x in recs]  # ... in every record, so the shape predicts
+        r[pos + 2] = ord("\n")
+    else:
+        r[pos] = ord("\n")
+    recs[k] = bytes(r)
+    out, _ = check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
+    assert out.status != 0 and out.n_records == k
+
+
+def test_prediction_high_bytes(torch, oracle, eng):
+    # a byte >= 0x80 in a quality line deep inside a predicted run (must not reach the dp4a addressing)
+    recs = [_plain_rec(b"h%06d" % i, 150, i) for i in range(5000)]
+    r = bytearray(recs[3777])
+    r[len(r) - 20] = 0xC3
+    recs[3777] = bytes(r)
+    check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
+
+
+# --------------------------------------------------------------------------------------------
 # shards: cut a small stream at EVERY byte; owner = shard where the record starts
 # --------------------------------------------------------------------------------------------
 def test_two_shards_every_cut(torch, oracle, eng):
