@@ -179,7 +179,7 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
     CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
     CKC(cudaMalloc(&ctx->d_ranges, sizeof(RangeInfo) * ctx->grid));
-    CKC(cudaMalloc(&ctx->d_sranges, sizeof(StreamRange) * ctx->grid * 32));
+    CKC(cudaMalloc(&ctx->d_sranges, sizeof(StreamRange) * ctx->grid * 32));   // (<= 32 warp ranges per CTA)
     CKC(cudaMalloc(&ctx->d_linecount, 8));
     CKC(cudaMalloc(&ctx->d_carry, sizeof(DevCarry)));
     CKC(cudaHostAlloc(&ctx->h_res, sizeof(DevResult), cudaHostAllocDefault));
@@ -260,12 +260,12 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     // the speculative kernel: 32 warp ranges per CTA, at least 8 KiB each; every range stages its line
     // ends in its own share of a staging area sized for lines of >= 16 bytes on average (a range that
     // needs more gives up and the exact path writes the index)
-    const bool fast = ctx->nchunk <= 5 && !getenv("FQB_NO_FAST");
+    const bool fast = ctx->nchunk <= 10 && !getenv("FQB_NO_FAST");
     uint64_t srange_bytes, stage_share = 0, n_sranges;
     {
         // equal ranges, rounded DOWN to 16 bytes; the last range takes the remainder (a little more work
         // for one warp, but a range too short to hold a few records could not infer its start)
-        const uint64_t nr = (uint64_t)ctx->grid * 32;
+        const uint64_t nr = (uint64_t)ctx->grid * stream_warps(ctx->nchunk);
         srange_bytes = sh->n_own / nr / 16 * 16;
         if (srange_bytes < 8192) srange_bytes = 8192;
         const uint64_t live = std::max<uint64_t>(1, std::min<uint64_t>(nr, sh->n_own / srange_bytes));
@@ -324,7 +324,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         // the speculative one, or the exact one when the speculative one is not used for this shape)
         if (fast) {
             if (timed) CK(cudaEventRecord(ctx->ev0, st));
-            CK(launch_stream(p, ctx->grid, st));
+            CK(launch_stream(p, ctx->nchunk, ctx->grid, st));
             if (timed) CK(cudaEventRecord(ctx->ev1, st));
             CK(launch_stream_verify(p, carry, st));
             ctx->launches += 2;

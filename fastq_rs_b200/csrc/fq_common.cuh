@@ -107,9 +107,9 @@ cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t s
 cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st);
 cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges, unsigned long long range_bytes,
                                cudaStream_t st);
-size_t stream_smem_bytes();
+int stream_warps(int nchunk);
 cudaError_t stream_configure();
-cudaError_t launch_stream(const ScanParams& p, int grid, cudaStream_t st);
+cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);

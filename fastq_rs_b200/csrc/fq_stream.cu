@@ -25,21 +25,25 @@
 
 namespace fq {
 
-template <int NCHUNK_>
+template <int NCHUNK_, int NWARPS_, int WIN_>
 struct SCfg {
     static constexpr int NCHUNK = NCHUNK_;
+    static constexpr int NWARPS = NWARPS_;                 // autonomous warps per CTA
+    static constexpr int NTHREADS = 32 * NWARPS_;
     static constexpr int PPAD = 32 * NCHUNK;
     static constexpr int CHUNK_WORDS = HIST_ROWS * 32;
     static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
-    static constexpr int WIN = 4096;                       // window bytes
+    static constexpr int WIN = WIN_;                       // window bytes (a multiple of 512)
     static constexpr int NU = WIN / UNIT;                  // 512-byte units per window
     static constexpr int LIST_N = 192;                     // u16 entries: [0] = cursor, [j] = start of the line after the j-th '\n'
     static constexpr int MAXR = (LIST_N - 12) / 4;         // records consumed per window at most
     static constexpr int LIST_DUMMY = LIST_N - 1;          // writes beyond the capacity land here
     static constexpr int WARP_BYTES = WIN + 16 + LIST_N * 2;
     static constexpr int TAIL_PAD = 256;                   // word loads of the rounds may run past the last buffer
-    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + 32 * WARP_BYTES + TAIL_PAD;
+    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + NWARPS * WARP_BYTES + TAIL_PAD;
+    static_assert(WIN % UNIT == 0 && WIN <= 65520, "window");
+    static_assert(TOTAL <= 232448 - 1024, "shared memory per CTA");
     static_assert(WARP_BYTES % 16 == 0, "TMA destination alignment");
 };
 
@@ -413,12 +417,12 @@ struct StreamCta {
 };
 
 template <class C>
-__global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
+__global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* lenh = hist + C::HIST_WORDS;
-    __shared__ unsigned long long bars[32];
+    __shared__ unsigned long long bars[C::NWARPS];
     __shared__ StreamCta cta;
 
     const int tid = threadIdx.x;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
     const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
 
-    for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += 1024) hist[i] = 0;
+    for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += C::NTHREADS) hist[i] = 0;
     if (lane == 0) mbar_init(&bars[warp], 1);
     if (tid == 0) {
         cta.n_records = 0;
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     }
 
     // the range of this warp: records that START in [R0, R1)
-    const uint32_t rid = blockIdx.x * 32u + (uint32_t)warp;
+    const uint32_t rid = blockIdx.x * (uint32_t)C::NWARPS + (uint32_t)warp;
     const unsigned long long R0 = (unsigned long long)rid * p.srange_bytes;
     const bool live = rid < p.n_sranges;
     // (the last range takes the remainder: a range too short to hold a few records could not infer its start)
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
     unsigned long long cur = 0, lrank = 0;
     bool failed = false;
     uint32_t my_epoch = 0;
-    constexpr int SLICE = (C::HIST_WORDS + 31) / 32;
+    constexpr int SLICE = (C::HIST_WORDS + C::NWARPS - 1) / C::NWARPS;
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
@@ -672,10 +676,10 @@ __global__ void __launch_bounds__(1024, 1) fq_stream_kernel(const __grid_constan
 
     // ---- drain -----------------------------------------------------------------------------
     __syncthreads();
-    flush_hist<C>(hist, p, 0, C::HIST_WORDS, tid, 1024);
+    flush_hist<C>(hist, p, 0, C::HIST_WORDS, tid, C::NTHREADS);
     {
         unsigned long long* lenh_g = p.stats + stats_len_off(p.max_len);
-        for (int i = tid; i < C::PPAD + 2; i += 1024) {
+        for (int i = tid; i < C::PPAD + 2; i += C::NTHREADS) {
             const uint32_t v = lenh[i];
             if (v) atomicAdd(lenh_g + i, (unsigned long long)v);
         }
@@ -759,19 +763,24 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-using SCfg5 = SCfg<5>;
+using SCfg5 = SCfg<5, 32, 4096>;     // P <= 160: 80 KB of counters, 32 warps x 4 KiB windows
+using SCfg10 = SCfg<10, 16, 3584>;   // P <= 320: 160 KB of counters, 16 warps x 3.5 KiB windows
 
-size_t stream_smem_bytes() { return (size_t)SCfg5::TOTAL; }
-uint32_t stream_window_bytes() { return (uint32_t)SCfg5::WIN; }
+int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }
 
 cudaError_t stream_configure()
 {
-    return cudaFuncSetAttribute(fq_stream_kernel<SCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg5::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<SCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg5::TOTAL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fq_stream_kernel<SCfg10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg10::TOTAL);
 }
 
-cudaError_t launch_stream(const ScanParams& p, int grid, cudaStream_t st)
+cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st)
 {
-    fq_stream_kernel<SCfg5><<<grid, 1024, SCfg5::TOTAL, st>>>(p);
+    if (nchunk <= 5)
+        fq_stream_kernel<SCfg5><<<grid, SCfg5::NTHREADS, SCfg5::TOTAL, st>>>(p);
+    else
+        fq_stream_kernel<SCfg10><<<grid, SCfg10::NTHREADS, SCfg10::TOTAL, st>>>(p);
     return cudaGetLastError();
 }
 
