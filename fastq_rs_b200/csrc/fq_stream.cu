@@ -23,6 +23,8 @@
 // (fq_scan.cu) redoes the shard.  Results never depend on the inference.
 #include "fq_hist.cuh"
 
+#include <cstdlib>
+
 namespace fq {
 
 template <int NCHUNK_, int NWARPS_, int WIN_>
@@ -36,7 +38,7 @@ struct SCfg {
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
     static constexpr int WIN = WIN_;                       // window bytes (a multiple of 512)
     static constexpr int NU = WIN / UNIT;                  // 512-byte units per window
-    static constexpr int LIST_N = 192;                     // u16 entries: [0] = cursor, [j] = start of the line after the j-th '\n'
+    static constexpr int LIST_N = WIN_ >= 4096 ? 192 : 128;   // u16 entries: [0] = cursor, [j] = start of the line after the j-th '\n'
     static constexpr int MAXR = (LIST_N - 12) / 4;         // records consumed per window at most
     static constexpr int LIST_DUMMY = LIST_N - 1;          // writes beyond the capacity land here
     static constexpr int WARP_BYTES = WIN + 16 + LIST_N * 2;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             const Window w = win_load<C>(p, buf, bar, parity, (long long)R0 - (front ? 1 : 0), lane);
             uint32_t hib;
             const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
-            const uint32_t nstored = min(total, (uint32_t)C::LIST_N - 2u);
+            const uint32_t nstored = min(total, (uint32_t)C::LIST_DUMMY - 1u);
             const uint32_t neg = (front && nstored >= 1u && list[1] == 16u) ? 1u : 0u;   // a '\n' right in front of the range
             uint32_t c;
             if (rid != 0 || (p.flags & F_INFER_START)) {
@@ -764,7 +766,8 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
 // launchers
 // ------------------------------------------------------------------------------------------
 using SCfg5 = SCfg<5, 32, 4096>;     // P <= 160: 80 KB of counters, 32 warps x 4 KiB windows
-using SCfg10 = SCfg<10, 16, 3584>;   // P <= 320: 160 KB of counters, 16 warps x 3.5 KiB windows
+using SCfg10 = SCfg<10, 22, 2560>;   // P <= 320: 160 KB of counters, 22 warps x 2.5 KiB windows (measured best of
+                                     // 16 x 3584 / 22 x 2560 / 26 x 2048 on fixed 300 bp and on 50..300 bp reads)
 
 int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }
 

@@ -11,5 +11,5 @@ FQB_TRACE=gpurun_out/trace.bin timeout 200 python tools/prof_one.py 4.0 1 1 150 
 python tools/trace_view.py gpurun_out/trace.bin 70 800 8 > gpurun_out/trace.txt 2>&1
 rm -f gpurun_out/trace.bin
 cat gpurun_out/trace.txt
-FQB_DEBUG=1 timeout 200 python tools/prof_var.py 4.0 1 1 3 > gpurun_out/prof_var.log 2>&1; tail -2 gpurun_out/prof_var.log
+timeout 200 python tools/prof_var.py 4.0 1 1 3 > gpurun_out/prof_var.log 2>&1; tail -1 gpurun_out/prof_var.log
 timeout 200 python tools/prof_one.py 4.0 1 1 300 3 > gpurun_out/prof_300.log 2>&1; tail -1 gpurun_out/prof_300.log
