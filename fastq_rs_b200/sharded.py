@@ -93,24 +93,29 @@ class ShardedParser:
         offsets of the '\\n' in [a, b))."""
         infer = sh.a != 0 and sh.b > sh.a
         out = self._parse(sh, hist, index, 0, infer)
-        # exact line numbers: prefix of the shards' newline counts (independent of the phase)
-        g = self._all_gather_words([out.n_lines, out.line_phase, out.status])
-        line_base = int(g[:self.rank, 0].sum())
-        if infer and (out.status == E_PHASE or out.line_phase != (line_base & 3)):
-            # not confirmed: n_lines of a shard whose chain verified is exact whatever the phase, and a
-            # shard that ended in E_PHASE has produced nothing -- count it, then parse with the exact base
-            self.reparsed += 1
-        need_count = bool((g[:, 2] == E_PHASE).any())
-        if need_count:
-            # some shard could not even deliver its newline count: every rank counts (cheap, exact)
+        # ONE all-gather in the common case: newline count (independent of the phase), inferred phase,
+        # and the outcome every rank needs for the first-error rule
+        def words(o):
+            return [o.status, o.err_offset, o.n_records, o.n_lines, int(o.finished), o.line_phase]
+        g = self._all_gather_words(words(out))
+        line_base = int(g[:self.rank, 3].sum())        # exact line number of this shard: prefix of n_lines
+        if bool((g[:, 0] == E_PHASE).any()):
+            # some shard could not even deliver its newline count: every rank counts (one cheap pass)
             view = sh.data[sh.front:] if sh.front else sh.data
-            n = self.eng.count_lines(view, sh.b - sh.a)
+            n = self.eng.count_lines(view, sh.b - sh.a) if sh.b > sh.a else 0
             g2 = self._all_gather_words([n])
             line_base = int(g2[:self.rank, 0].sum())
-        if infer and (out.status == E_PHASE or out.line_phase != (line_base & 3)):
+        unconfirmed = infer and (out.status == E_PHASE or out.line_phase != (line_base & 3))
+        if unconfirmed:
+            # the inference is not confirmed: parse again with the exact line number
+            self.reparsed += 1
             out = self._parse(sh, hist, index, line_base, False)
+        # did anybody parse again?  (every rank can tell from the gathered phases and counts)
+        lb = np.concatenate([[0], np.cumsum(g[:-1, 3])]) if not bool((g[:, 0] == E_PHASE).any()) else None
+        anybody = bool((g[:, 0] == E_PHASE).any()) or bool(((g[1:, 5] & 3) != (lb[1:] & 3)).any())
+        if anybody:
+            g = self._all_gather_words(words(out))
         # first error in stream order wins; shards behind it contribute nothing
-        g = self._all_gather_words([out.status, out.err_offset, out.n_records, out.n_lines, int(out.finished)])
         bad = np.nonzero(g[:, 0] != OK)[0]
         first_bad = int(bad[0]) if bad.size else None
         stats_dev = self.eng.device_stats()
