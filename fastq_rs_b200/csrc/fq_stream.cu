@@ -241,13 +241,14 @@ struct SRounds {
     // inc_s / inc_q: 1 / 0x10000 for lanes with a record, 0 for the others (their bumps add nothing)
     static __device__ __forceinline__ void run(uint32_t as0, uint32_t aq0, uint32_t shs, uint32_t shq, uint32_t ns,
                                                uint32_t nq, uint32_t nmax_w, uint32_t nmin_w, uint32_t inc_s,
-                                               uint32_t inc_q, uint32_t hist_s, const LaneK& lc)
+                                               uint32_t inc_q, uint32_t hist_s, const LaneK& lc, uint32_t& hib)
     {
         if (32u * T >= nmax_w) return;                                    // warp-uniform
         const uint32_t s0 = lds32<32 * T>(as0), s1 = lds32<32 * T + 4>(as0);
         const uint32_t q0 = lds32<32 * T>(aq0), q1 = lds32<32 * T + 4>(aq0);
         const uint32_t vs = __funnelshift_r(s0, s1, shs);
         const uint32_t vq = __funnelshift_r(q0, q1, shq);
+        hib |= vs | vq;                                                   // (see pred_pass: bytes >= 0x80)
         constexpr int CO = 4 * C::CHUNK_WORDS * T;                        // byte offset of chunk T
         if (32u * (T + 1) <= nmin_w) {                                    // every record's group lies inside both lines
 #pragma unroll
@@ -265,13 +266,13 @@ struct SRounds {
                 if ((int)lc.hk[k] < tq) red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
             }
         }
-        SRounds<C, T + 1>::run(as0, aq0, shs, shq, ns, nq, nmax_w, nmin_w, inc_s, inc_q, hist_s, lc);
+        SRounds<C, T + 1>::run(as0, aq0, shs, shq, ns, nq, nmax_w, nmin_w, inc_s, inc_q, hist_s, lc, hib);
     }
 };
 template <class C>
 struct SRounds<C, C::NCHUNK> {
     static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                                               uint32_t, uint32_t, uint32_t, uint32_t, const LaneK&)
+                                               uint32_t, uint32_t, uint32_t, uint32_t, const LaneK&, uint32_t&)
     {
     }
 };
@@ -337,8 +338,9 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
         const uint32_t nmin_w = __reduce_min_sync(0xffffffffu, ok ? min(ns, nq) : 0xFFFFFFFFu);
         const uint32_t sa = buf_s + h + 1u + 4u * i;       // shared address of position 4i of the sequence line
         const uint32_t qa = buf_s + pp + 1u + 4u * i;      // (buf_s is 16-byte aligned; the funnel shift takes sa * 8 mod 32)
+        uint32_t hib_unused = 0;   // (the scan has looked at every byte of the window already)
         SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, nmax_w, nmin_w, ok ? 1u : 0u, ok ? 0x10000u : 0u,
-                           hist_s, lc);
+                           hist_s, lc, hib_unused);
         // positions beyond the shared-memory columns but below P: straight to global (P > PPAD only)
         if (p.max_len > Pm && ok) {
             const uint32_t gs = min(Ls, p.max_len), gq = min(Lq, p.max_len);
@@ -374,7 +376,7 @@ template <class C>
 __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, uint32_t pad, uint32_t chk_off,
                                               uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t nq,
                                               const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
-                                              uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB)
+                                              uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
 {
     const uint32_t r = 4u * pass + sub;
     const bool valid = r < n_rec;
@@ -394,22 +396,12 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     const uint32_t sa = s + sh.Lh + 4u * i;                    // position 4i of the sequence line
     const uint32_t qa = sa + sh.Lsq + sh.Lp;                   // ... of the quality line
     // lanes without a (holding) record do not hold the fast rounds back: their bumps add zero
+    // hib: OR of every word the rounds look at.  A byte >= 0x80 makes the dp4a address leave its row --
+    // still inside this CTA's shared memory (at most 32 KB above the table: the length histogram and
+    // window buffers), so nothing faults; the caller raises spec_fail and the exact path redoes the shard.
     SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ok ? ns : 0u, ok ? nq : 0u, max(ns, nq), min(ns, nq),
-                       ok ? 1u : 0u, ok ? 0x10000u : 0u, hist_s, lc);
+                       ok ? 1u : 0u, ok ? 0x10000u : 0u, hist_s, lc, hib);
     return first_bad;
-}
-
-// OR of all words of the window (bytes >= 0x80 must not reach the dp4a addressing of the rounds)
-template <class C>
-__device__ __forceinline__ bool win_has_high_bytes(uint32_t buf_s, int lane)
-{
-    uint32_t hib = 0;
-#pragma unroll
-    for (int it = 0; it < C::NU; ++it) {
-        const uint4 v = lds_v4(buf_s + (uint32_t)(it * UNIT + lane * 16));
-        hib |= v.x | v.y | v.z | v.w;
-    }
-    return __any_sync(0xffffffffu, (hib & 0x80808080u) != 0);
 }
 
 struct StreamCta {
@@ -540,10 +532,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             // ---- predicted window: full, inside the owned bytes, at least one record ------------------
             const uint32_t n_fit = (uint32_t)(C::WIN - w.pad) / sh.reclen;
             if (predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own) {
-                if (win_has_high_bytes<C>(buf_s, lane)) {
-                    failed = true;   // bytes >= 0x80: the exact path
-                    break;
-                }
                 // records that start inside the range
                 n_rec = n_fit;
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
@@ -555,10 +543,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t chk_neg = (li == 6 && !sh.cr_s) || (li == 7 && !sh.cr_q) ? 1u : 0u;
                 const uint32_t Lr = sh.Lsq - 1u;
                 const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;       // seq()/qual() drop one trailing '\r'
-                uint32_t first_bad = NO_START;
+                uint32_t first_bad = NO_START, hib = 0;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
                     first_bad = pred_pass<C>(buf_s, sh, w.pad, chk_off, chk_exp, chk_neg, Ls, Lq, lc, hist_s, n_rec, pass,
-                                             sub, li, kA, kB);
+                                             sub, li, kA, kB, hib);
+                if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                    failed = true;   // bytes >= 0x80 reached the rounds: the exact path
+                    break;
+                }
                 if (first_bad != NO_START) {
                     // the prediction stops holding at this record: consume what came before it, scan next time
                     n_rec = first_bad;
