@@ -35,6 +35,18 @@ REC_BYTES = 17 + 2 * (READ_LEN + 1) + 2  # 321
 GIB = 1 << 30
 
 
+def profiled_traffic(gib: float):
+    """dram read + write bytes per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/), valid for the workload it was captured on (16 GiB)."""
+    path = os.path.join(ROOT, "profiles", "r01_stream_kernel_ncu_full_16GiB.txt")
+    if abs(gib - 16.0) > 1e-9 or not os.path.exists(path):
+        return None
+    for line in open(path):
+        if line.startswith("traffic = dram read + write per launch"):
+            return float(line.split()[-1])
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -240,7 +252,9 @@ def run_ours(args):
     alg_bytes = n_own + 16 * (n_own // REC_BYTES)            # 1 B read per input byte + 16 B index per record
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5>>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": args.traffic_bytes, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": args.traffic_bytes if args.traffic_bytes is not None else profiled_traffic(args.gib),
+                "traffic_source": "ncu --set full, profiles/r01_stream_kernel_ncu_full_16GiB.txt", "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes}
 
     # ---- end to end through the host API (rank-local; pinned host bytes) ---------------------

@@ -262,8 +262,8 @@ struct SRounds {
             const int ts = (int)hist_s + 4 * ((int)ns - 32 * T), tq = (int)hist_s + 4 * ((int)nq - 32 * T);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if ((int)lc.hk[k] < ts) red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), 1u);
-                if ((int)lc.hk[k] < tq) red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), 0x10000u);
+                if ((int)lc.hk[k] < ts) red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), inc_s);
+                if ((int)lc.hk[k] < tq) red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), inc_q);
             }
         }
         SRounds<C, T + 1>::run(as0, aq0, shs, shq, ns, nq, nmax_w, nmin_w, inc_s, inc_q, hist_s, lc, hib);
@@ -399,8 +399,10 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     // hib: OR of every word the rounds look at.  A byte >= 0x80 makes the dp4a address leave its row --
     // still inside this CTA's shared memory (at most 32 KB above the table: the length histogram and
     // window buffers), so nothing faults; the caller raises spec_fail and the exact path redoes the shard.
-    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ok ? ns : 0u, ok ? nq : 0u, max(ns, nq), min(ns, nq),
-                       ok ? 1u : 0u, ok ? 0x10000u : 0u, hist_s, lc, hib);
+    // (ns, nq are the same for every record of the window: the guards of the last, partial round do
+    // not depend on the pass, only the increments do)
+    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, max(ns, nq), min(ns, nq), ok ? 1u : 0u,
+                       ok ? 0x10000u : 0u, hist_s, lc, hib);
     return first_bad;
 }
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# one GPU visit: parity tests, bench (ours + reference arm), ncu launch list + one full capture of the scan kernel
+# one GPU visit: smoke, parity tests, bench (ours + reference arm), ncu launch list + one full capture of the stream kernel
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt; lscpu | grep "Model name" >> gpurun_out/gpu.txt
