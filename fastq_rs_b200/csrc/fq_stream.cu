@@ -751,8 +751,20 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
     for (uint32_t r = blockIdx.x; r < nlive; r += gridDim.x) {
         const StreamRange sr = p.sranges[r];
         const uint32_t* src = p.index_stage + (size_t)r * p.stage_share;
-        for (unsigned long long i = threadIdx.x; i < sr.n_lines; i += blockDim.x)
-            if (sr.rank0 + i < p.index_cap) p.index[sr.rank0 + i] = src[i];
+        // (source and destination are shifted against each other by an arbitrary number of entries,
+        // so this stays a 4-byte copy; four loads in flight per thread keep the memory system busy)
+        const unsigned long long n = min(sr.n_lines, p.index_cap > sr.rank0 ? p.index_cap - sr.rank0 : 0ull);
+        uint32_t* dst = p.index + sr.rank0;
+        unsigned long long i = threadIdx.x;
+        for (; i + 3ull * blockDim.x < n; i += 4ull * blockDim.x) {
+            const uint32_t a = __ldg(src + i), b = __ldg(src + i + blockDim.x), c = __ldg(src + i + 2 * blockDim.x),
+                           d = __ldg(src + i + 3 * blockDim.x);
+            dst[i] = a;
+            dst[i + blockDim.x] = b;
+            dst[i + 2 * blockDim.x] = c;
+            dst[i + 3 * blockDim.x] = d;
+        }
+        for (; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
     }
 }
 
