@@ -269,19 +269,52 @@ class Parser:
         return results
 
     # ---- fast paths: nothing but counts / histograms ever reaches the host -------------------
+    def _stream(self, hist: bool):
+        """Feed the reader through the pinned ring (the thread_reader protocol, src/thread_reader.rs:
+        40-50 and 126-147): a reader thread fills pinned slots straight from `reader.readinto` --
+        acquire = empty_recv.recv(), submit = full_send.send() -- while the copy stream and the
+        kernels drain the slots behind it.  In-memory inputs skip the thread and go through
+        fqb_parse_host."""
+        r = self._reader
+        if isinstance(r, (bytes, bytearray, memoryview, np.ndarray)) or not hasattr(r, "readinto"):
+            data = _read_all(r)
+            outcome, st, _ = self._engine.parse_host(data, hist=hist, want_stats=hist)
+            return outcome, st
+        eng = self._engine
+        eng.stream_begin(hist=hist)
+        err: list = []
+
+        def pump():
+            try:
+                while True:
+                    slot = eng.stream_acquire()                  # blocks until a pinned slot is free
+                    n = r.readinto(memoryview(slot).cast("B"))   # one read per slot, may be short
+                    eng.stream_submit(n or 0)
+                    if not n:
+                        return
+            except BaseException as e:                           # reader errors travel to the caller
+                err.append(e)
+
+        t = threading.Thread(target=pump, name="reader-thread")
+        t.start()
+        t.join()
+        if err:
+            try:
+                eng.stream_finish(want_stats=False)
+            finally:
+                raise err[0]
+        return eng.stream_finish(want_stats=hist)
+
     def count(self) -> int:
         """examples/fastq-count.rs: number of records (raises on bad input)."""
-        data = _read_all(self._reader)
-        outcome, _, _ = self._engine.parse_host(data, hist=False, want_stats=False)
+        outcome, _ = self._stream(hist=False)
         outcome.raise_for_status()
         return outcome.n_records
 
     def stats(self) -> tuple[Outcome, Stats]:
         """The stats closure (per-position base / quality histograms over seq()/qual()) run on the
         GPU; Outcome.status tells whether (and where) each() would have returned Err."""
-        data = _read_all(self._reader)
-        outcome, st, _ = self._engine.parse_host(data, hist=True)
-        return outcome, st
+        return self._stream(hist=True)
 
 
 def each_zipped(parser1: Parser, parser2: Parser, callback) -> tuple[bool, bool]:

@@ -564,6 +564,35 @@ def test_streaming_small_slots(fq, oracle):
         e.close()
 
 
+def test_fastq_count_example_on_a_10mb_file(fq, oracle, tmp_path):
+    """BASELINE config 1 (examples/fastq-count.rs on a 10 MB synthetic 150 bp file: 31 152 records),
+    through parse_path -> Parser.count() (reader thread -> pinned ring -> kernels) and through
+    Parser.each with a counting closure; plus Parser.stats() streamed from the file."""
+    import subprocess
+    import sys
+    n_rec = 31152
+    data = oracle.synth_fixed_records(n_rec).tobytes()
+    assert len(data) == 9999792
+    path = tmp_path / "reads.fastq"
+    path.write_bytes(data)
+    assert fq.parse_path(str(path), lambda parser: parser.count()) == n_rec
+    seen = []
+    assert fq.parse_path(str(path), lambda parser: parser.each(lambda r: seen.append(len(r.seq())) or True)) is True
+    assert len(seen) == n_rec and set(seen) == {150}
+    out, st = fq.parse_path(str(path), lambda parser: parser.stats())
+    _, ost = oracle.each_stats(data, 150)
+    assert out.status == 0 and out.n_records == n_rec
+    assert_stats_equal(st, ost)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = subprocess.check_output([sys.executable, os.path.join(root, "examples", "fastq_count.py"), str(path)], text=True)
+    assert int(got.strip()) == n_rec
+    # a truncated file raises the reference's error after counting nothing more
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes(data[:-1])
+    with pytest.raises(fq.FastqError, match="truncated"):
+        fq.parse_path(str(bad), lambda parser: parser.count())
+
+
 # --------------------------------------------------------------------------------------------
 # property test: random valid FASTQ, randomly mutated (reference fuzz targets, fuzz/fuzz_targets/*.rs)
 # --------------------------------------------------------------------------------------------
