@@ -524,6 +524,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         // shape of the last record delimited by a scan: while it keeps predicting the following
         // records, windows are not scanned at all (see pred_pass)
         Shape sh = {0, 0, 0, 0, 0, 1};
+        // per-lane constants of the shape (set with it): the byte this lane verifies in every record,
+        // the line end this lane writes to the index, and how many records fit a window
+        uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0;
         bool predict = false;
         uint32_t strikes = 0, cooldown = 0;
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
@@ -532,17 +535,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             const unsigned long long room = R1 - w.src;          // > pad: window bytes inside the range
             uint32_t n_rec, n_lines, next;
             // ---- predicted window: full, inside the owned bytes, at least one record ------------------
-            const uint32_t n_fit = (uint32_t)(C::WIN - w.pad) / sh.reclen;
+            const uint32_t n_fit = nfit_max - (w.pad > nfit_rem ? 1u : 0u);   // = (WIN - pad) / reclen
             if (predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own) {
                 // records that start inside the range
                 n_rec = n_fit;
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
-                // the byte every lane verifies per record (relative to the record start)
-                const uint32_t o2 = sh.Lh + sh.Lsq;
-                const uint32_t chk_off = li == 0 ? 0u : li == 1 ? sh.Lh - 1u : li == 2 ? o2 - 1u : li == 3 ? o2
-                                       : li == 4 ? o2 + sh.Lp - 1u : li == 5 ? sh.reclen - 1u : li == 6 ? o2 - 2u : sh.reclen - 2u;
-                const uint32_t chk_exp = li == 0 ? '@' : li == 3 ? '+' : li >= 6 ? '\r' : '\n';
-                const uint32_t chk_neg = (li == 6 && !sh.cr_s) || (li == 7 && !sh.cr_q) ? 1u : 0u;
                 const uint32_t Lr = sh.Lsq - 1u;
                 const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;       // seq()/qual() drop one trailing '\r'
                 uint32_t first_bad = NO_START, hib = 0;
@@ -575,9 +572,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                         break;
                     }
                     // lane = 4 * (record mod 8) + line: the line-end offset is fixed per lane
-                    const uint32_t k = (uint32_t)lane & 3u;
-                    const uint32_t le = k == 0 ? sh.Lh - 1u : k == 1 ? o2 - 1u : k == 2 ? o2 + sh.Lp - 1u : sh.reclen - 1u;
-                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + le;
+                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + idx_le;
                     uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
                     for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
                 }
@@ -626,6 +621,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     if (cooldown) --cooldown;
                     predict = (p.flags & F_HIST) && cooldown == 0 && sh.Lsq - 1u <= Pm && sh.Lh >= 2u && sh.Lh <= 64u &&
                               sh.Lp >= 2u && sh.Lp <= 34u;
+                    if (predict) {
+                        const uint32_t o2 = sh.Lh + sh.Lsq;
+                        // the byte lane li of a record's 8 lanes verifies (relative to the record start)
+                        chk_off = li == 0 ? 0u : li == 1 ? sh.Lh - 1u : li == 2 ? o2 - 1u : li == 3 ? o2
+                                : li == 4 ? o2 + sh.Lp - 1u : li == 5 ? sh.reclen - 1u : li == 6 ? o2 - 2u : sh.reclen - 2u;
+                        chk_exp = li == 0 ? '@' : li == 3 ? '+' : li >= 6 ? '\r' : '\n';
+                        chk_neg = (li == 6 && !sh.cr_s) || (li == 7 && !sh.cr_q) ? 1u : 0u;
+                        const uint32_t k = (uint32_t)lane & 3u;
+                        idx_le = k == 0 ? sh.Lh - 1u : k == 1 ? o2 - 1u : k == 2 ? o2 + sh.Lp - 1u : sh.reclen - 1u;
+                        nfit_max = (uint32_t)C::WIN / sh.reclen;
+                        nfit_rem = (uint32_t)C::WIN - nfit_max * sh.reclen;
+                    }
                 }
                 // line ends of the consumed records that lie in the owned bytes of the shard
                 n_lines = 4u * n_rec;
