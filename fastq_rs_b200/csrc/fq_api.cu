@@ -271,7 +271,9 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         const uint64_t live = std::max<uint64_t>(1, std::min<uint64_t>(nr, sh->n_own / srange_bytes));
         n_sranges = live;
         if (fast && want_index) {
-            stage_share = 2 * srange_bytes / 16 + 64;
+            // (lines of >= 16 bytes on average; the last range is longer by the remainder)
+            const uint64_t rem = sh->n_own > live * srange_bytes ? sh->n_own - live * srange_bytes : 0;
+            stage_share = (srange_bytes + rem) / 16 + 64;
             const uint64_t need = live * stage_share;
             if (need > ctx->index_stage_cap) {
                 if (ctx->d_index_stage) {
