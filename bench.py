@@ -56,23 +56,50 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region.  The region is tens of milliseconds long,
+    so the samples come from NVML directly (one every ~2 ms); `nvidia-smi` (the B200_PROFILING.md
+    recipe; ~100 ms per call) is the fallback when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv = (pynvml, h, float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.source = "nvml"
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        nv, h, mx = self._nv
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.rows.append([sm, mx, None] + ["Active" if r & bits[k] else "Not Active" for k in
+                                           ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nv is not None:
+                    self._sample_nvml()
+                    self._stop.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -91,13 +118,13 @@ class ClockSampler:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
-            except ValueError:
+            except (ValueError, TypeError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def gen_host_sample(n_bytes: int, threads: int) -> np.ndarray:
