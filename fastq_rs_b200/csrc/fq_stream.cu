@@ -291,7 +291,7 @@ __device__ __forceinline__ bool no_newline32(uint32_t buf_s, uint32_t from, uint
 
 // One pass over 4 records whose line starts come from the scan's list.  Returns the window-relative
 // number of the first record of the pass that failed validation (NO_START if none did).
-template <class C>
+template <class C, bool HIST>
 __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8_t* buf, uint32_t buf_s,
                                                 const LaneK& lc, uint32_t hist_s, uint32_t* lenh, uint32_t Pm,
                                                 uint32_t n_rec, uint32_t pass, WinAcc& wa, uint32_t sub, uint32_t i)
@@ -312,7 +312,7 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
         const unsigned nok = __ballot_sync(0xffffffffu, valid && !good);
         if (nok) first_bad = 4u * pass + (((uint32_t)__ffs(nok) - 1u) >> 3);
     }
-    if (p.flags & F_HIST) {
+    if (HIST) {
         uint32_t Ls = 0, Lq = 0;
         if (ok) {
             const uint32_t Lr = q - h - 1u;
@@ -406,13 +406,38 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     return first_bad;
 }
 
+// '\n' count of a full window at positions >= pad (no list, no ranks: ~1/3 of the scan)
+template <class C>
+__device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t pad, int lane, uint32_t kA, uint32_t kB)
+{
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int it = 0; it < C::NU; ++it) {
+        const uint4 v = lds_v4(buf_s + (uint32_t)(it * UNIT + lane * 16));
+        uint32_t m0 = nlbits3(v.x, kA, kB), m1 = nlbits3(v.y, kA, kB), m2 = nlbits3(v.z, kA, kB), m3 = nlbits3(v.w, kA, kB);
+        if (it == 0 && lane == 0) {                                       // bytes before the cursor
+            const uint32_t pw = pad >> 2, pb = (pad & 3u) * 8u;           // whole words / bytes of the next word to drop
+            const uint32_t part = ~((1u << pb) - 1u);
+            m0 = pw > 0 ? 0u : m0 & part;
+            m1 = pw > 1 ? 0u : (pw == 1 ? m1 & part : m1);
+            m2 = pw > 2 ? 0u : (pw == 2 ? m2 & part : m2);
+            m3 = pw == 3 ? m3 & part : m3;
+        }
+        // the flags sit at bit 7 of every byte: one popc over the four words, shifted apart
+        cnt += (uint32_t)__popc(m0 | (m1 >> 1) | (m2 >> 2) | (m3 >> 3));
+    }
+    return __reduce_add_sync(0xffffffffu, cnt);
+}
+
 struct StreamCta {
     uint32_t n_records, n_bases;   // totals of the CTA (u32: a CTA sees < 4 G bases per launch; native shared atomics)
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
     uint32_t flush_epoch;
 };
 
-template <class C>
+// HIST: the launch accumulates the per-position histograms (FQB_F_HIST); the two variants share no
+// hot code (rounds + '\n'-row check vs. newline count), so each is compiled without the other's registers
+template <class C, bool HIST>
 __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -536,7 +561,50 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             uint32_t n_rec, n_lines, next;
             // ---- predicted window: full, inside the owned bytes, at least one record ------------------
             const uint32_t n_fit = nfit_max - (w.pad > nfit_rem ? 1u : 0u);   // = (WIN - pad) / reclen
-            if (predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own) {
+            const bool can_predict = predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own;
+            if (can_predict && !HIST) {
+                // ---- no histograms: the window holds n_fit predicted records and the head of the next.
+                // All their predicted line ends (and '@', '+') are verified byte by byte, and the window
+                // must hold exactly that many '\n': together that leaves no room for a stray one.
+                const uint32_t E = w.pad + n_fit * sh.reclen;                 // start of the partial record
+                const uint32_t o2 = sh.Lh + sh.Lsq;
+                const uint32_t tail = (uint32_t)C::WIN - E;                   // its bytes in the window
+                const uint32_t n_tail = (tail >= sh.Lh ? 1u : 0u) + (tail >= o2 ? 1u : 0u) + (tail >= o2 + sh.Lp ? 1u : 0u);
+                const uint32_t total = win_count_newlines<C>(buf_s, w.pad, lane, kA, kB);
+                bool good = total == 4u * n_fit + n_tail;
+                const uint32_t n_chk = 6u * n_fit + n_tail;                   // '@', 4 x '\n', '+' per record; '\n' of the tail
+                for (uint32_t j = lane; j < n_chk; j += 32) {
+                    uint32_t rec = j / 6u, k = j - 6u * rec;
+                    if (rec >= n_fit) {                                       // the line ends of the partial record
+                        k = 1u + (j - 6u * n_fit) + ((j - 6u * n_fit) >= 2u ? 1u : 0u);   // -> k = 1, 2, 4
+                        rec = n_fit;
+                    }
+                    const uint32_t off = k == 0 ? 0u : k == 1 ? sh.Lh - 1u : k == 2 ? o2 - 1u : k == 3 ? o2
+                                       : k == 4 ? o2 + sh.Lp - 1u : sh.reclen - 1u;
+                    const uint32_t want = k == 0 ? '@' : k == 3 ? '+' : '\n';
+                    good = good && lds_u8(buf_s + w.pad + rec * sh.reclen + off) == want;
+                }
+                if (!__all_sync(0xffffffffu, good)) {
+                    predict = false;                                          // scan this window instead
+                    if (++strikes >= 2) cooldown = 32;
+                    continue;
+                }
+                strikes = 0;
+                n_rec = n_fit;                                                // records that start inside the range
+                if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
+                if (lane == 0) atomicAdd(&cta.n_records, n_rec);
+                n_lines = 4u * n_rec;
+                next = w.pad + n_rec * sh.reclen;
+                if (want_index) {
+                    if (lrank + n_lines > p.stage_share) {
+                        failed = true;   // staging share too small: the exact path writes the index
+                        break;
+                    }
+                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + idx_le;
+                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
+                    for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
+                }
+            } else if (can_predict) {
                 // records that start inside the range
                 n_rec = n_fit;
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
@@ -596,7 +664,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 WinAcc wa = {0, 0};
                 uint32_t first_bad = NO_START;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = stream_pass<C>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
+                    first_bad = stream_pass<C, HIST>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
                     failed = true;   // a record that fails validation: the exact path finds and classifies it
                     break;
@@ -619,8 +687,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     sh.cr_s = (sh.Lsq > 1u && buf[l2 - 2u] == '\r') ? 1u : 0u;
                     sh.cr_q = (sh.Lsq > 1u && buf[l4 - 2u] == '\r') ? 1u : 0u;
                     if (cooldown) --cooldown;
-                    predict = (p.flags & F_HIST) && cooldown == 0 && sh.Lsq - 1u <= Pm && sh.Lh >= 2u && sh.Lh <= 64u &&
-                              sh.Lp >= 2u && sh.Lp <= 34u;
+                    // with histograms: every byte of the sequence / quality lines must have a counter (the
+                    // '\n' row is what checks them) and header / separator are checked 32 bytes at a time;
+                    // without: the '\n' count of the window checks every line, any shape will do
+                    predict = cooldown == 0 && sh.Lh >= 2u && sh.Lp >= 2u &&
+                              (HIST ? (sh.Lsq - 1u <= Pm && sh.Lh <= 64u && sh.Lp <= 34u) : true);
                     if (predict) {
                         const uint32_t o2 = sh.Lh + sh.Lsq;
                         // the byte lane li of a record's 8 lanes verifies (relative to the record start)
@@ -784,19 +855,36 @@ using SCfg10 = SCfg<10, 22, 2560>;   // P <= 320: 160 KB of counters, 22 warps x
 
 int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }
 
+template <class C>
+static cudaError_t configure_pair()
+{
+    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fq_stream_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
+}
+
 cudaError_t stream_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<SCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg5::TOTAL);
+    cudaError_t e = configure_pair<SCfg5>();
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fq_stream_kernel<SCfg10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg10::TOTAL);
+    return configure_pair<SCfg10>();
+}
+
+template <class C>
+static void launch_pair(const ScanParams& p, int grid, cudaStream_t st)
+{
+    if (p.flags & F_HIST)
+        fq_stream_kernel<C, true><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+    else
+        fq_stream_kernel<C, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
 }
 
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st)
 {
     if (nchunk <= 5)
-        fq_stream_kernel<SCfg5><<<grid, SCfg5::NTHREADS, SCfg5::TOTAL, st>>>(p);
+        launch_pair<SCfg5>(p, grid, st);
     else
-        fq_stream_kernel<SCfg10><<<grid, SCfg10::NTHREADS, SCfg10::TOTAL, st>>>(p);
+        launch_pair<SCfg10>(p, grid, st);
     return cudaGetLastError();
 }
 
