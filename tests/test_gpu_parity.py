@@ -391,6 +391,61 @@ def test_prediction_high_bytes(torch, oracle, eng):
     check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
 
 
+def check_count_mode(torch, oracle, engine, data: bytes):
+    """delimit + index WITHOUT histograms (the predicting delimiter then verifies a window by its
+    '\n' count instead of the histogram's '\n' row) == oracle.each on the same bytes."""
+    t = to_dev(torch, data)
+    idx = torch.zeros(len(data) + 8, dtype=torch.int32, device="cuda")
+    for index in (idx, None):
+        engine.parse_device(t, n_own=len(data), n_avail=len(data), hist=False, index=index)
+        out, _ = engine.fetch(want_stats=False)
+        ores, orecs = oracle.each(data)
+        assert (out.status, out.n_records) == (ores.status, ores.n_records), (out, ores)
+        if ores.status != 0:
+            assert out.err_offset == ores.err_offset
+        assert out.n_lines == data.count(b"\n")
+    _, oidx = oracle.each_index(data)
+    n = out.n_records
+    got = idx[:4 * n].cpu().numpy().view(np.uint32).astype(np.uint64).reshape(n, 4)
+    np.testing.assert_array_equal(got, oidx[:, 1:5])
+    return out
+
+
+@pytest.mark.parametrize("where", ["none", "seq", "qual", "header", "sep", "at", "plus"])
+def test_count_mode_prediction(where, torch, oracle, eng):
+    recs = [_plain_rec(b"id%07d" % i, 150, i) for i in range(6000)]
+    k = 4321
+    r = bytearray(recs[k])
+    hl = len(b"id%07d" % k) + 2
+    if where == "seq":
+        r[hl + 77] = ord("\n")
+    elif where == "qual":
+        r[hl + 151 + 2 + 40] = ord("\n")
+    elif where == "header":
+        r[5] = ord("\n")
+    elif where == "sep":
+        recs = [x.replace(b"\n+\n", b"\n+ab\n") for x in recs]
+        r = bytearray(recs[k])
+        r[hl + 151 + 2] = ord("\n")
+    elif where == "at":
+        r[0] = ord("A")
+    elif where == "plus":
+        r[hl + 151] = ord("-")
+    recs[k] = bytes(r)
+    out = check_count_mode(torch, oracle, eng, b"".join(recs))
+    assert (out.status != 0 and out.n_records == k) if where != "none" else out.n_records == 6000
+
+
+def test_count_mode_varying_shapes(torch, oracle, eng):
+    data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
+    check_count_mode(torch, oracle, eng, data)
+    data = b"".join(_plain_rec(b"c%06d" % i, 120, i, eol=b"\r\n") for i in range(4000))
+    check_count_mode(torch, oracle, eng, data)
+    # long reads with a window-filling shape: one record per 2560 / 4096-byte window and longer
+    data = b"".join(_plain_rec(b"L%05d" % i, L, i) for i, L in enumerate([900, 900, 900, 1900, 1900, 2040, 2040, 5000, 900] * 40))
+    check_count_mode(torch, oracle, eng, data)
+
+
 # --------------------------------------------------------------------------------------------
 # shards: cut a small stream at EVERY byte; owner = shard where the record starts
 # --------------------------------------------------------------------------------------------
