@@ -270,8 +270,10 @@ struct SRounds {
             const int ts = (int)hist_s + 4 * ((int)ns - 32 * T), tq = (int)hist_s + 4 * ((int)nq - 32 * T);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if ((int)lc.hk[k] < ts) red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), inc_s);
-                if ((int)lc.hk[k] < tq) red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), inc_q);
+                // branch-free: a byte beyond its line bumps by zero (a branch around the asm costs a
+                // divergence region per bump; the address stays inside the table for bytes < 0x80)
+                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), (int)lc.hk[k] < ts ? inc_s : 0u);
+                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), (int)lc.hk[k] < tq ? inc_q : 0u);
             }
         }
         SRounds<C, T + 1>::run(as0, aq0, shs, shq, ns, nq, nmax_w, nmin_w, inc_s, inc_q, hist_s, lc, hib);
