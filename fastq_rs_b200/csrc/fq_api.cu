@@ -32,6 +32,8 @@ __global__ void fq_init_kernel(DevResult* r, int spec_fail, int line_phase)
     r->finished = 0;
     r->spec_fail = spec_fail;   // 1: no speculative launch, go straight to the exact path
     r->line_phase = line_phase;
+    r->n_win_pred = 0;
+    r->n_win_scan = 0;
 }
 
 struct Slot {  // one stage of the streaming ring
@@ -395,7 +397,9 @@ int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
             fclose(f);
         }
     }
-    if (getenv("FQB_DEBUG")) fprintf(stderr, "fastq_b200: spec_fail=%d status=%d\n", ctx->h_res->spec_fail, ctx->h_res->status);
+    if (getenv("FQB_DEBUG"))
+        fprintf(stderr, "fastq_b200: spec_fail=%d status=%d windows predicted=%llu scanned=%llu\n", ctx->h_res->spec_fail,
+                ctx->h_res->status, ctx->h_res->n_win_pred, ctx->h_res->n_win_scan);
     fill_result(ctx->h_res, ctx->last_off, res);
     return FQB_OK;
 }

@@ -36,6 +36,8 @@ struct DevResult {
     int finished;
     int spec_fail;                  // the speculative kernel did not deliver: the exact path redoes the shard
     int line_phase;                 // line_base mod 4 implied by the first record start of the shard
+    unsigned long long n_win_pred;  // windows of the speculative kernel that were predicted / scanned (FQB_DEBUG)
+    unsigned long long n_win_scan;
 };
 
 // one contiguous range of tiles = the work of one CTA

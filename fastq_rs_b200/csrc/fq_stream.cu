@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0;
         bool predict = false;
         uint32_t strikes = 0, cooldown = 0;
+        uint32_t dbg_pred = 0, dbg_scan = 0;
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
         while (!failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
@@ -600,6 +601,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     continue;
                 }
                 strikes = 0;
+                ++dbg_pred;
                 n_rec = n_fit;                                                // records that start inside the range
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
                 if (lane == 0) atomicAdd(&cta.n_records, n_rec);
@@ -636,6 +638,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 } else {
                     strikes = 0;
                 }
+                ++dbg_pred;
                 if (n_rec == 0) continue;
                 if (lane == 0) {
                     atomicAdd(&cta.n_records, n_rec);
@@ -656,6 +659,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 }
             } else {
                 // ---- scanned window -------------------------------------------------------------------
+                ++dbg_scan;
                 uint32_t hib;
                 const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
                 const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
@@ -754,6 +758,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             sr.end = cur;
             sr.n_lines = lrank;
             sr.flags = failed ? 2u : 1u;
+            atomicAdd(&p.res->n_win_pred, (unsigned long long)dbg_pred);
+            atomicAdd(&p.res->n_win_scan, (unsigned long long)dbg_scan);
             if (failed) atomicExch(&p.res->spec_fail, 1);
         }
     }
