@@ -446,6 +446,42 @@ def test_count_mode_varying_shapes(torch, oracle, eng):
     check_count_mode(torch, oracle, eng, data)
 
 
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_prediction_fuzz(seed, torch, oracle, eng, eng300):
+    """Runs of records with a constant shape (what the predicting delimiter feeds on) glued together
+    with shape changes, CRLF blocks, text after '+', and -- in two thirds of the seeds -- one
+    anomaly somewhere: the GPU result must equal the oracle's in histogram mode and in count mode."""
+    rng = np.random.default_rng(1000 + seed)
+    recs = []
+    n_target = int(rng.integers(4000, 9000))
+    i = 0
+    while len(recs) < n_target:
+        run = int(rng.integers(1, 900))
+        L = int(rng.choice([0, 1, 3, 36, 75, 100, 150, 151, 200, 250, 299, 300]))
+        hl = int(rng.integers(1, 70))
+        eol = b"\r\n" if rng.random() < 0.2 else b"\n"
+        sep_txt = bytes(rng.integers(65, 91, size=int(rng.integers(0, 40))).astype(np.uint8)) if rng.random() < 0.2 else b""
+        for _ in range(run):
+            head = (b"%d" % i).ljust(hl, b"x")[:max(hl, 1)]
+            seq = bytes(b"ACGTN"[int(x)] for x in rng.integers(0, 5, size=L))
+            qual = bytes(rng.integers(33, 75, size=L).astype(np.uint8))
+            recs.append(b"@" + head + eol + seq + eol + b"+" + sep_txt + eol + qual + eol)
+            i += 1
+    kind = seed % 3
+    if kind:
+        k = int(rng.integers(1, len(recs)))
+        r = bytearray(recs[k])
+        pos = int(rng.integers(0, len(r) - 1))
+        r[pos] = {1: 10, 2: int(rng.choice([0x80, 0xFF, 13, 64, 43]))}[kind]
+        recs[k] = bytes(r)
+    data = b"".join(recs)
+    if seed % 4 == 3:
+        data = data[:-int(rng.integers(1, 200))]                # truncated tail
+    engine = eng300 if seed % 2 else eng
+    check_device_vs_oracle(torch, oracle, engine, data, check_index=True)
+    check_count_mode(torch, oracle, engine, data)
+
+
 # --------------------------------------------------------------------------------------------
 # shards: cut a small stream at EVERY byte; owner = shard where the record starts
 # --------------------------------------------------------------------------------------------
