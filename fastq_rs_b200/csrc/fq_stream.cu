@@ -634,7 +634,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     // the prediction stops holding at this record: consume what came before it, scan next time
                     n_rec = first_bad;
                     predict = false;
-                    if (first_bad == 0 && ++strikes >= 2) cooldown = 32;   // (variable-length reads: stop trying for a while)
+                    // (reads or headers of varying length: after two predictions that did not even get
+                    // through half of their window, stop trying for a while)
+                    if (2u * first_bad < n_fit && ++strikes >= 2) cooldown = 32;
                 } else {
                     strikes = 0;
                 }
