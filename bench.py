@@ -364,9 +364,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=16.0, help="GiB of FASTQ per GPU")
-    ap.add_argument("--e2e-gib", type=float, default=4.0,
+    ap.add_argument("--e2e-gib", type=float, default=None,
                     help="GiB per GPU streamed from pinned host memory in the e2e leg (PCIe-bound: the rate does not "
-                         "depend on the size; a prefix of the same shard keeps pinning time and host RAM bounded at N=8)")
+                         "depend on the size); default: the whole 16 GiB shard at N=1, a 4 GiB prefix of every shard at N>1 "
+                         "(keeps pinning time and pinned host RAM bounded at N=8)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--slot-mib", type=int, default=64)
     ap.add_argument("--cpu-sample-gib", type=float, default=2.0)
@@ -375,6 +376,8 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes/launch from the committed ncu --set full capture (profiles/)")
     args = ap.parse_args()
+    if args.e2e_gib is None:
+        args.e2e_gib = 16.0 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 4.0
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
