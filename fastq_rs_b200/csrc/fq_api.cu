@@ -62,6 +62,7 @@ struct fqb_ctx {
     uint64_t* d_stats = nullptr;
     uint64_t* d_seqraw = nullptr;
     DevResult* d_res = nullptr;
+    unsigned long long* d_pub = nullptr;   // outcome of the last parse as 8 device words (fqb_device_result)
     RangeInfo* d_ranges = nullptr;
     StreamRange* d_sranges = nullptr;
     uint32_t* d_index_stage = nullptr;  // speculative launch: per-range staging of the line ends
@@ -181,6 +182,8 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
     CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
     CKC(cudaMalloc(&ctx->d_ranges, sizeof(RangeInfo) * ctx->grid));
+    CKC(cudaMalloc(&ctx->d_pub, 8 * sizeof(unsigned long long)));
+    CKC(cudaMemset(ctx->d_pub, 0, 8 * sizeof(unsigned long long)));
     CKC(cudaMalloc(&ctx->d_sranges, sizeof(StreamRange) * ctx->grid * 32));   // (<= 32 warp ranges per CTA)
     CKC(cudaMalloc(&ctx->d_linecount, 8));
     CKC(cudaMalloc(&ctx->d_carry, sizeof(DevCarry)));
@@ -229,6 +232,7 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_seqraw);
     cudaFree(ctx->d_res);
     cudaFree(ctx->d_ranges);
+    cudaFree(ctx->d_pub);
     cudaFree(ctx->d_sranges);
     cudaFree(ctx->d_index_stage);
     cudaFree(ctx->d_linecount);
@@ -357,7 +361,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             ctx->launches += 1;
         }
     }
-    CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), st));
+    CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), carry ? nullptr : ctx->d_pub, st));
     ctx->launches += 1;
     return FQB_OK;
 }
@@ -405,6 +409,7 @@ int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
 }
 
 uint64_t* fqb_device_stats(fqb_ctx* ctx) { return ctx ? ctx->d_stats : nullptr; }
+uint64_t* fqb_device_result(fqb_ctx* ctx) { return ctx ? reinterpret_cast<uint64_t*>(ctx->d_pub) : nullptr; }
 uint64_t fqb_launch_count(fqb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 float fqb_last_scan_ms(fqb_ctx* ctx)

@@ -114,7 +114,8 @@ cudaError_t stream_configure();
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
-cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st);
+cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, unsigned long long* pub,
+                            cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);
 cudaError_t launch_synth_fixed(uint8_t* out, unsigned long long n, unsigned long long byte_off, uint32_t L,
                                unsigned long long seed, cudaStream_t st);

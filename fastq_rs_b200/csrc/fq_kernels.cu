@@ -155,7 +155,8 @@ __global__ void fq_range_prefix_kernel(const ScanParams p, const DevCarry* carry
 
 // fold the raw sequence-byte histogram into the six base classes (validate_dnan's alphabet,
 // src/records.rs:29-33), publish the outcome, and (streaming) add the chunk into the totals
-__global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned long long* total)
+__global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned long long* total,
+                                   unsigned long long* pub)
 {
     const uint32_t P = p.max_len;
     const bool skip = carry && carry->status != 0;  // stream failed in an earlier chunk
@@ -195,6 +196,16 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
             if ((p.flags & F_INFER_START) && r->spec_fail) r->status = 7;
             r->n_records = p.stats[0];
             r->finished = r->status == 0 ? 1 : 0;
+            if (pub) {   // the outcome as 8 device-resident words (fqb_device_result)
+                pub[0] = (unsigned long long)r->status;
+                pub[1] = (unsigned long long)r->finished;
+                pub[2] = r->n_records;
+                pub[3] = r->n_lines;
+                pub[4] = r->err_offset;
+                pub[5] = r->tail_start == NONE64 ? NONE64 : p.stream_offset + r->tail_start;
+                pub[6] = (unsigned long long)r->line_phase;
+                pub[7] = 0;
+            }
             if (carry) {
                 carry->n_records += p.stats[0];
                 carry->n_lines += r->n_lines;
@@ -365,9 +376,10 @@ cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges
     return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, cudaStream_t st)
+cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, unsigned long long* pub,
+                            cudaStream_t st)
 {
-    fq_finalize_kernel<<<64, 256, 0, st>>>(p, carry, total);
+    fq_finalize_kernel<<<64, 256, 0, st>>>(p, carry, total, pub);
     return cudaGetLastError();
 }
 

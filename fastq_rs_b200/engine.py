@@ -141,16 +141,27 @@ class Engine:
         return Outcome(int(res.status), bool(res.finished), int(res.n_records), int(res.n_lines),
                        int(res.err_offset), tail, int(res.line_phase))
 
-    def device_stats(self):
-        """The device-resident stats block of the last parse as an int64 CUDA tensor view
-        (same bits as u64; for an in-place all_reduce)."""
+    def _device_view(self, ptr: int, n_words: int):
         import torch
-        ptr = self.L.fqb_device_stats(self.ctx)
 
         class _Arr:
-            __cuda_array_interface__ = {"shape": (self.n_words,), "typestr": "<i8",
-                                        "data": (ptr, False), "version": 3}
+            __cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         return torch.as_tensor(_Arr(), device=f"cuda:{self.device}")
+
+    def device_stats(self):
+        """The device-resident stats block of the last parse as an int64 CUDA tensor view
+        (same bits as u64; for an all_reduce)."""
+        if getattr(self, "_stats_view", None) is None:
+            self._stats_view = self._device_view(self.L.fqb_device_stats(self.ctx), self.n_words)
+        return self._stats_view
+
+    def device_result(self):
+        """The outcome of the last parse_device as 8 device-resident int64 words
+        [status, finished, n_records, n_lines, err_offset, tail_offset, line_phase, 0] -- valid in
+        stream order after the parse; lets the N-rank driver all-gather outcomes without a host sync."""
+        if getattr(self, "_result_view", None) is None:
+            self._result_view = self._device_view(self.L.fqb_device_result(self.ctx), 8)
+        return self._result_view
 
     def count_lines(self, d_bytes, n: int | None = None, stream=None) -> int:
         n = d_bytes.numel() if n is None else n

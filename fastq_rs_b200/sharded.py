@@ -87,14 +87,58 @@ class ShardedParser:
                               front16=(sh.front == 16), eof=sh.is_last, infer_start=infer)
         return self.eng.fetch(want_stats=False)[0]
 
+    def _enqueue(self, sh: ShardSpec, hist, index, line_base, infer):
+        """parse_device without waiting for it"""
+        view = sh.data[sh.front:] if sh.front else sh.data
+        if sh.b == sh.a:
+            self.eng.parse_device(view, n_own=0, n_avail=0, hist=hist, index=None, line_base=line_base,
+                                  stream_offset=sh.a, line_start=False, front16=False, eof=sh.is_last)
+        else:
+            self.eng.parse_device(view, n_own=sh.b - sh.a, n_avail=sh.b - sh.a + sh.halo, hist=hist, index=index,
+                                  line_base=line_base, stream_offset=sh.a, line_start=(sh.a == 0),
+                                  front16=(sh.front == 16), eof=sh.is_last, infer_start=infer)
+
     def parse(self, sh: ShardSpec, hist: bool = True, index=None):
         """Delimit (+histograms) the whole stream; every rank returns the GLOBAL (Outcome, Stats).
         `index` (optional int32 tensor) receives this rank's line ends (low 32 bits of the stream
-        offsets of the '\\n' in [a, b))."""
+        offsets of the '\n' in [a, b)).
+
+        Common case = ONE host synchronisation: the parse, an all-gather of the 8-word device-resident
+        outcomes, and an all-reduce of a copy of the statistics block are enqueued back to back; the
+        host then reads both.  Only if some outcome shows an error, an unconfirmed inference or
+        FQB_E_PHASE is the careful path below taken (the local statistics block is still intact)."""
+        import torch
         infer = sh.a != 0 and sh.b > sh.a
-        out = self._parse(sh, hist, index, 0, infer)
-        # ONE all-gather in the common case: newline count (independent of the phase), inferred phase,
-        # and the outcome every rank needs for the first-error rule
+        fast = hasattr(self.eng, "device_result") and self.dist is not None and self.world > 1
+        if fast:
+            self._enqueue(sh, hist, index, 0, infer)
+            res_all = torch.empty(self.world * 8, dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(res_all, self.eng.device_result(), group=self.group)
+            summed = self.eng.device_stats().clone()
+            self.dist.all_reduce(summed, op=self.dist.ReduceOp.SUM, group=self.group)
+            g8 = res_all.cpu().numpy().reshape(self.world, 8)          # the one synchronisation
+            lb = np.concatenate([[0], np.cumsum(g8[:-1, 3])])          # exact line numbers: prefix of n_lines
+            if bool((g8[:, 0] == OK).all()) and self._phases_ok(g8, lb):
+                words = summed.cpu().numpy().view(np.uint64).copy()
+                total = Outcome(status=OK, finished=bool(g8[-1, 1]), n_records=int(g8[:, 2].sum()),
+                                n_lines=int(g8[:, 3].sum()), err_offset=0, tail_offset=None, line_phase=0)
+                return total, Stats(self.eng.max_len, words)
+            out = self.eng.fetch(want_stats=False)[0]
+        else:
+            out = self._parse(sh, hist, index, 0, infer)
+        return self._careful(sh, hist, index, infer, out)
+
+    def _phases_ok(self, g8, lb) -> bool:
+        """every inferring shard (all but the first, unless it owns nothing) reports the phase its exact
+        line number has; shards that own nothing (n_lines == 0 and n_records == 0) are exempt"""
+        for r in range(1, self.world):
+            empty = g8[r, 3] == 0 and g8[r, 2] == 0
+            if not empty and (int(g8[r, 6]) & 3) != (int(lb[r]) & 3):
+                return False
+        return True
+
+    def _careful(self, sh, hist, index, infer, out):
+        """The general protocol: confirm or redo the inference, first error in stream order wins."""
         def words(o):
             return [o.status, o.err_offset, o.n_records, o.n_lines, int(o.finished), o.line_phase]
         g = self._all_gather_words(words(out))
@@ -123,7 +167,7 @@ class ShardedParser:
             stats_dev.zero_()
         if self.dist is not None and self.world > 1:
             self.dist.all_reduce(stats_dev, op=self.dist.ReduceOp.SUM, group=self.group)
-        words = stats_dev.cpu().numpy().view(np.uint64).copy()
+        stats_words = stats_dev.cpu().numpy().view(np.uint64).copy()
         upto = self.world if first_bad is None else first_bad + 1
         total = Outcome(status=int(g[first_bad, 0]) if first_bad is not None else OK,
                         finished=first_bad is None and bool(g[-1, 4]),
@@ -131,4 +175,4 @@ class ShardedParser:
                         n_lines=int(g[:, 3].sum()),
                         err_offset=int(g[first_bad, 1]) if first_bad is not None else 0,
                         tail_offset=None, line_phase=0)
-        return total, Stats(self.eng.max_len, words)
+        return total, Stats(self.eng.max_len, stats_words)

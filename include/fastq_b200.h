@@ -145,6 +145,11 @@ int fqb_fetch_line_count(fqb_ctx *ctx, void *stream, uint64_t *n_lines);
 int fqb_fetch(fqb_ctx *ctx, void *stream, fqb_result *res, uint64_t *host_stats);
 /* device address of the stats block of the last parse (for an in-place allreduce) */
 uint64_t *fqb_device_stats(fqb_ctx *ctx);
+/* device address of the outcome of the last fqb_parse_device as 8 words, valid once the kernels of
+ * that parse have run (stream order): [0] status [1] finished [2] n_records [3] n_lines
+ * [4] err_offset [5] tail_offset (UINT64_MAX if none) [6] line_phase [7] reserved -- lets an N-rank
+ * driver all-gather the outcomes without a host round trip */
+uint64_t *fqb_device_result(fqb_ctx *ctx);
 /* number of kernels this library launched on ctx so far (bench accounting) */
 uint64_t fqb_launch_count(fqb_ctx *ctx);
 /* CUDA-event time of the main scan kernel of the last fqb_parse_device call, in ms

@@ -28,6 +28,16 @@ class FakeEngine:
         self.n_parses = 0
         self._stats = torch.zeros(8 + max_len + 2 + 6 * max_len + 256 * max_len, dtype=torch.int64)
         self._out = None
+        self._res = torch.zeros(8, dtype=torch.int64)
+
+    def device_result(self):
+        """the 8-word outcome block of fqb_device_result"""
+        return self._res
+
+    def _publish(self, o):
+        self._out = o
+        self._res[:] = torch.tensor([o.status, int(o.finished), o.n_records, o.n_lines, o.err_offset,
+                                     -1 if o.tail_offset is None else o.tail_offset, o.line_phase, 0], dtype=torch.int64)
 
     def count_lines(self, view, n):
         return int((view[:n].numpy() == 10).sum())
@@ -72,7 +82,7 @@ class FakeEngine:
 
         if infer_start:
             if self.fail_infer:
-                self._out = Outcome(E_PHASE, False, 0, 0, 0, None, 0)
+                self._publish(Outcome(E_PHASE, False, 0, 0, 0, None, 0))
                 return
             good = []
             for K in ([0, 1, 2, 3] if at_ls else [1, 2, 3, 4]):
@@ -83,7 +93,7 @@ class FakeEngine:
                 if st == 0 and n >= 2:
                     good.append(K)
             if len(good) != 1:
-                self._out = Outcome(E_PHASE, False, 0, 0, 0, None, 0)
+                self._publish(Outcome(E_PHASE, False, 0, 0, 0, None, 0))
                 return
             K = good[0]
             phase = (4 - K) & 3
@@ -100,4 +110,4 @@ class FakeEngine:
         if n_rec:
             _, st = oracle.each_stats(buf[s:end].tobytes(), self.max_len)
             self._stats[:] = torch.from_numpy(stats_words(self.max_len, st, n_rec).view(np.int64))
-        self._out = Outcome(status, status == 0, n_rec, n_lines, err, None, phase)
+        self._publish(Outcome(status, status == 0, n_rec, n_lines, err, None, phase))
