@@ -16,7 +16,7 @@ ABI_VERSION = 2
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
 E_ARG, E_STATE, E_NOMEM, E_CUDA = 50, 51, 52, 100
-F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START, F_PARTIAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 MAX_RECORD_BYTES = 68 * 1024
 SYNTH_SEED = 0xFA57A11CE5EED001
 NO_OFFSET = 0xFFFFFFFFFFFFFFFF

@@ -90,6 +90,7 @@ struct fqb_ctx {
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     bool streaming = false;
     uint32_t stream_flags = 0;
+    bool stream_partial = false; // FQB_F_PARTIAL: the last chunk is not the end of the stream
     uint64_t chunk_no = 0;       // chunks submitted to the device
     uint64_t fill = 0;           // bytes filled in the current host slot
     uint64_t stream_pos = 0;     // stream offset of the current host slot's first byte
@@ -525,6 +526,7 @@ int fqb_stream_begin(fqb_ctx* ctx, uint32_t flags)
     CK(cudaMemsetAsync(ctx->d_carry, 0, sizeof(DevCarry), ctx->s_comp));
     ctx->streaming = true;
     ctx->stream_flags = flags & (FQB_F_HIST | FQB_F_INDEX);
+    ctx->stream_partial = false;
     ctx->chunk_no = 0;
     ctx->fill = 0;
     ctx->stream_pos = 0;
@@ -549,7 +551,7 @@ static int launch_pending(fqb_ctx* ctx, uint64_t next_bytes, bool eof)
     sh.n_avail = ctx->pending_bytes + std::min<uint64_t>(next_bytes, MAXREC);
     sh.stream_offset = ctx->pending_off;
     sh.flags = ctx->stream_flags | (ctx->pending_line_start ? FQB_F_LINE_START : 0) |
-               ((eof && next_bytes <= MAXREC) ? FQB_F_EOF : 0);
+               ((eof && next_bytes <= MAXREC && !ctx->stream_partial) ? FQB_F_EOF : 0);
     if (ctx->stream_flags & FQB_F_INDEX) {
         DevSlot& d = ctx->dslots[ds];
         if (!d.d_index) CK(cudaMalloc(&d.d_index, (size_t)ctx->slot_bytes * 4));
@@ -653,11 +655,11 @@ static int stream_drain(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
     CK(cudaStreamSynchronize(ctx->s_comp));
     CK(cudaStreamSynchronize(ctx->s_copy));
     res->status = ctx->h_carry->status;
-    res->finished = ctx->h_carry->status == 0;
+    res->finished = ctx->h_carry->status == 0 && ctx->h_carry->tail_plus1 == 0;
     res->n_records = ctx->h_carry->n_records;
     res->n_lines = ctx->h_carry->n_lines;
     res->err_offset = ctx->h_carry->err_offset;
-    res->tail_offset = UINT64_MAX;
+    res->tail_offset = ctx->h_carry->tail_plus1 ? ctx->h_carry->tail_plus1 - 1 : UINT64_MAX;
     res->line_phase = 0;
     res->reserved = 0;
     ctx->streaming = false;
@@ -692,6 +694,7 @@ int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint32_t flag
     if (rc) return rc;
     ctx->host_index = host_index;
     ctx->host_index_cap = host_index ? index_cap : 0;
+    ctx->stream_partial = (flags & FQB_F_PARTIAL) != 0;
     // pinned caller memory is copied from directly; pageable memory goes through the pinned slots
     cudaPointerAttributes attr;
     bool pinned = false;

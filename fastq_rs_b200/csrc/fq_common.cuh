@@ -66,6 +66,7 @@ struct DevCarry {
     unsigned long long n_lines;
     int status;                     // sticky first error
     int pad;
+    unsigned long long tail_plus1;  // 1 + stream offset of the first incomplete-not-bad record (0 = none)
 };
 
 struct ScanParams {

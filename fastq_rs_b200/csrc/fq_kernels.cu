@@ -210,6 +210,8 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
                 carry->n_records += p.stats[0];
                 carry->n_lines += r->n_lines;
                 carry->line_base = r->line_end;
+                if (r->tail_start != NONE64 && carry->tail_plus1 == 0)
+                    carry->tail_plus1 = p.stream_offset + r->tail_start + 1;
                 if (r->status != 0) {
                     carry->status = r->status;
                     carry->err_offset = r->err_offset;

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (E_HEADER, E_LENGTH, E_PHASE, E_SEP, E_TOO_LONG, E_TRUNCATED, F_EOF, F_FRONT16, F_HIST,
-                   F_INDEX, F_INFER_START, F_LINE_START, OK)
+                   F_INDEX, F_INFER_START, F_LINE_START, F_PARTIAL, OK)
 
 
 class FastqError(ValueError):
@@ -185,10 +185,12 @@ class Engine:
         return int(self.L.fqb_launch_count(self.ctx))
 
     # ---- host path -------------------------------------------------------------------------
-    def parse_host(self, data, *, hist: bool = True, want_index: bool = False, want_stats: bool = True):
+    def parse_host(self, data, *, hist: bool = True, want_index: bool = False, want_stats: bool = True,
+                   partial: bool = False):
         """Delimit (+histograms) host bytes end to end through the pinned ring.
         `data`: bytes-like / uint8 ndarray / (address, nbytes).  Returns (Outcome, Stats|None, index|None)
-        where index = u64 stream offsets of every line end."""
+        where index = u64 stream offsets of every line end.  `partial`: one refill of a longer stream
+        (FQB_F_PARTIAL): an incomplete trailing record is reported in Outcome.tail_offset, not as an error."""
         if isinstance(data, tuple):
             addr, n = data
             keep = None
@@ -200,7 +202,7 @@ class Engine:
         words = np.zeros(self.n_words, dtype=np.uint64) if want_stats else None
         idx = np.empty(max(n, 1), dtype=np.uint32) if want_index else None
         n_idx = C.c_uint64(0)
-        flags = (F_HIST if hist else 0) | (F_INDEX if want_index else 0)
+        flags = (F_HIST if hist else 0) | (F_INDEX if want_index else 0) | (F_PARTIAL if partial else 0)
         _check(self.ctx, self.L.fqb_parse_host(
             self.ctx, addr, n, flags, C.byref(res), words.ctypes.data if want_stats else None,
             idx.ctypes.data if want_index else None, idx.size if want_index else 0, C.byref(n_idx)),

@@ -14,6 +14,10 @@ plus the fast paths that never materialise records on the host: Parser.count(), 
 
 Record delimiting ('\n' scan, '@'/'+'/length validation, record offsets) always runs on the GPU
 through the C ABI; closures run here over the returned index, borrowing the caller's bytes.
+
+Readers are consumed in refills of `chunk_bytes` (bounded memory, like the reference's Buffer --
+src/buffer.rs:51-100 -- at a GPU-sized granularity): each refill is delimited with FQB_F_PARTIAL,
+and the incomplete record at its end is carried over in front of the next one (Buffer::clean).
 """
 from __future__ import annotations
 
@@ -26,6 +30,7 @@ import numpy as np
 from .engine import Engine, FastqError, Outcome, Stats
 
 BUFSIZE = 68 * 1024  # src/lib.rs:129
+CHUNK_BYTES = 32 << 20  # refill size of the generic-closure path (the reference refills 68 KiB at a time)
 
 _default_engines: dict = {}
 
@@ -144,10 +149,30 @@ def _read_all(reader) -> np.ndarray:
     return np.frombuffer(b"".join(chunks), dtype=np.uint8)
 
 
-class _Delimited:
-    """Result of the GPU delimiting pass over one stream: record starts and line ends."""
+def _fill(reader, view: np.ndarray) -> int:
+    """Read until `view` is full or the reader is exhausted (short reads are topped up, the loop of
+    src/buffer.rs:74-100); returns the bytes read."""
+    got = 0
+    mv = memoryview(view)
+    while got < len(mv):
+        if hasattr(reader, "readinto"):
+            n = reader.readinto(mv[got:])
+        else:
+            b = reader.read(len(mv) - got)
+            n = len(b)
+            mv[got:got + n] = b
+        if not n:
+            break
+        got += n
+    return got
 
-    def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray):
+
+class _Delimited:
+    """Result of the GPU delimiting pass over one refill of the stream: record starts and line ends
+    (relative to `data`); `base` = stream offset of data[0], `delivered` = records of earlier refills."""
+
+    def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray, base: int = 0, delivered: int = 0):
+        self.base, self.delivered = base, delivered
         n = outcome.n_records
         ends = index[:4 * n].astype(np.int64).reshape(n, 4)
         starts = np.empty(n, dtype=np.int64)
@@ -157,18 +182,29 @@ class _Delimited:
         self.buf = memoryview(data)
         self.outcome, self.starts, self.ends = outcome, starts, ends
 
+    def raise_for_status(self) -> None:
+        o = self.outcome
+        if o.status != 0:
+            raise FastqError(o.status, self.base + o.err_offset, self.delivered + o.n_records)
+
 
 class RecordRefIter:  # src/lib.rs:241-304
-    def __init__(self, d: _Delimited):
-        self._d, self._i, self._cur = d, -1, None
+    def __init__(self, chunks: Iterator[_Delimited]):
+        self._chunks, self._d, self._i, self._cur, self._done = iter(chunks), None, -1, None, False
 
     def advance(self) -> None:
-        self._i += 1
-        if self._i < len(self._d.starts):
-            self._cur = _make_record(self._d.buf, int(self._d.starts[self._i]), self._d.ends[self._i])
-        else:
-            self._cur = None
-            self._d.outcome.raise_for_status()  # Err only after every earlier record was handed out
+        self._cur = None
+        while not self._done:
+            if self._d is not None:
+                self._i += 1
+                if self._i < len(self._d.starts):
+                    self._cur = _make_record(self._d.buf, int(self._d.starts[self._i]), self._d.ends[self._i])
+                    return
+                if self._d.outcome.status != 0:
+                    self._done = True
+                    self._d.raise_for_status()  # Err only after every earlier record was handed out
+            self._d, self._i = next(self._chunks, None), -1   # refill (src/lib.rs:262-294)
+            self._done = self._d is None
 
     def get(self) -> Optional[RefRecord]:
         return self._cur
@@ -178,17 +214,42 @@ class Parser:
     """Parser::new(reader) (src/lib.rs:200).  `reader`: bytes-like, uint8 ndarray, or an object
     with .read().  `max_len` = positions tracked by stats()."""
 
-    def __init__(self, reader, engine: Optional[Engine] = None, max_len: int = 150):
+    def __init__(self, reader, engine: Optional[Engine] = None, max_len: int = 150,
+                 chunk_bytes: int = CHUNK_BYTES):
         self._reader = reader
         self._engine = engine or default_engine(max_len)
+        self._chunk_bytes = max(1, int(chunk_bytes))
 
-    def _delimit(self) -> _Delimited:
-        data = _read_all(self._reader)
-        outcome, _, index = self._engine.parse_host(data, hist=False, want_index=True, want_stats=False)
-        return _Delimited(data, outcome, index)
+    def _chunks(self) -> Iterator[_Delimited]:
+        """Delimit the stream refill by refill.  In-memory inputs are one refill; a reader is consumed
+        `chunk_bytes` at a time with the incomplete record at the end of a refill carried over in front
+        of the next (Buffer::clean, src/buffer.rs:51-72), so memory stays bounded by chunk_bytes + one
+        record.  A refill that reports an error is the last one."""
+        r, eng = self._reader, self._engine
+        if isinstance(r, (bytes, bytearray, memoryview, np.ndarray)):
+            data = _read_all(r)
+            outcome, _, index = eng.parse_host(data, hist=False, want_index=True, want_stats=False)
+            yield _Delimited(data, outcome, index)
+            return
+        left = np.empty(0, dtype=np.uint8)
+        base = delivered = 0
+        ch = self._chunk_bytes
+        while True:
+            buf = np.empty(left.size + ch, dtype=np.uint8)
+            buf[:left.size] = left
+            n = _fill(r, buf[left.size:])
+            eof = n < ch
+            buf = buf[:left.size + n]
+            outcome, _, index = eng.parse_host(buf, hist=False, want_index=True, want_stats=False,
+                                               partial=not eof)
+            yield _Delimited(buf, outcome, index, base, delivered)
+            if eof or outcome.status != 0:
+                return
+            t = buf.size if outcome.tail_offset is None else outcome.tail_offset
+            left, base, delivered = buf[t:], base + t, delivered + outcome.n_records
 
     def ref_iter(self) -> RecordRefIter:
-        return RecordRefIter(self._delimit())
+        return RecordRefIter(self._chunks())
 
     def each(self, func: Callable[[RefRecord], bool]) -> bool:
         """Apply func to every record; stop if it returns False.  Returns True at end of input,
@@ -207,17 +268,17 @@ class Parser:
         """Batches of records whose bytes span at most BUFSIZE (src/lib.rs:364-425).  As in the
         reference, an error surfaces when the batch holding the bad record would be produced,
         and that batch is dropped."""
-        d = self._delimit()
-        n = len(d.starts)
-        i = 0
-        while i < n:
-            j = int(np.searchsorted(d.ends[:, 3], d.starts[i] + BUFSIZE - 1, side="right"))
-            j = max(j, i + 1)
-            if j >= n and d.outcome.status != 0:
-                break  # the batch that would end at the bad record is dropped (src/lib.rs:375,399-410)
-            yield RecordSet(d.buf, d.starts[i:j], d.ends[i:j])
-            i = j
-        d.outcome.raise_for_status()
+        for d in self._chunks():
+            n = len(d.starts)
+            i = 0
+            while i < n:
+                j = int(np.searchsorted(d.ends[:, 3], d.starts[i] + BUFSIZE - 1, side="right"))
+                j = max(j, i + 1)
+                if j >= n and d.outcome.status != 0:
+                    break  # the batch that would end at the bad record is dropped (src/lib.rs:375,399-410)
+                yield RecordSet(d.buf, d.starts[i:j], d.ends[i:j])
+                i = j
+            d.raise_for_status()
 
     def parallel_each(self, n_threads: int, func: Callable[[Iterator[RecordSet]], object]) -> list:
         """n_threads workers, each fed RecordSets round-robin over a bounded queue of 10

@@ -63,6 +63,13 @@ enum {
                                    depend on the phase) and parses again with the exact line_base
                                    on a mismatch or on FQB_E_PHASE.                             */
 
+#define FQB_F_PARTIAL     0x40u /* fqb_parse_host only: more bytes of the stream follow the bytes of this
+                                   call (a refill is pending, src/lib.rs:262-294): a trailing record
+                                   that is incomplete -- and shorter than FQB_MAX_RECORD_BYTES -- is
+                                   not an error; fqb_result.tail_offset reports where it starts so
+                                   that the caller carries it over in front of the next bytes, as
+                                   Buffer::clean does (src/buffer.rs:51-72)                      */
+
 typedef struct fqb_ctx fqb_ctx;
 
 typedef struct {
@@ -159,7 +166,10 @@ float fqb_last_scan_ms(fqb_ctx *ctx);
 /* ---- host path: bytes in host memory, staged through the pinned ring --------------------
  * replaces Parser::new(reader).each(stats closure) end to end.  Synchronous.
  * host_index (optional): receives the low 32 bits of the stream offset of every '\n'
- * before the first bad record, up to index_cap entries; *n_index = entries written. */
+ * before the first bad record, up to index_cap entries; *n_index = entries written.
+ * flags: FQB_F_HIST | FQB_F_INDEX | FQB_F_PARTIAL.  With FQB_F_PARTIAL the call is one refill of a
+ * longer stream (bounded-memory each()/record_sets(): src/lib.rs:262-294, 364-425): offsets are
+ * relative to `bytes`, which must start at a record start. */
 int fqb_parse_host(fqb_ctx *ctx, const uint8_t *bytes, uint64_t n, uint32_t flags,
                    fqb_result *res, uint64_t *host_stats,
                    uint32_t *host_index, uint64_t index_cap, uint64_t *n_index);

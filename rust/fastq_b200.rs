@@ -17,6 +17,7 @@ use std::slice;
 pub const FQB_ABI_VERSION: u32 = 2;
 pub const FQB_F_HIST: u32 = 0x01;
 pub const FQB_F_INDEX: u32 = 0x02;
+pub const FQB_F_PARTIAL: u32 = 0x40; // one refill of a longer stream: tail_offset instead of a truncation error
 
 #[repr(C)]
 pub struct FqbConfig {

@@ -655,6 +655,78 @@ def test_streaming_small_slots(fq, oracle):
         e.close()
 
 
+class _ShortReader:
+    """A reader that returns short, ragged reads (no readinto)."""
+
+    def __init__(self, data: bytes, with_readinto: bool):
+        self._b, self._k = io.BytesIO(data), 0
+        if with_readinto:
+            self.readinto = self._readinto
+
+    def read(self, n):
+        self._k += 1
+        return self._b.read(min(n, 1 + (self._k * 7919) % 30011))
+
+    def _readinto(self, mv):
+        b = self.read(len(mv))
+        mv[:len(b)] = b
+        return len(b)
+
+
+@pytest.mark.parametrize("chunk", [1, 4097, 70000, 1 << 20])
+def test_each_over_a_reader_in_refills(chunk, fq, oracle, eng):
+    """Bounded-memory generic-closure path: the reader is consumed `chunk` bytes at a time
+    (FQB_F_PARTIAL + carry-over of the incomplete trailing record); records, order and the error
+    -- kind, stream offset, records delivered before it -- equal the oracle's each()."""
+    recs = [_rec(i, L) for i, L in enumerate([150, 0, 3, 150, 60000, 151, 150, 1, 30000, 150] * (1 if chunk < 4097 else 6))]
+    good = b"".join(recs)
+    if chunk == 1:
+        good = b"".join(_rec(i, L) for i, L in enumerate([3, 0, 5]))
+    cases = [good, good[:-1], good + b"\n", good[:len(good) // 2] + b"X" + good[len(good) // 2:], good + b"@tail\nAC\n"]
+    if chunk > 1:
+        cases.append(good + _rec(99, 40000) + _rec(100, 5))   # a record that is too long, seen across refills
+    for k, data in enumerate(cases):
+        ores, oidx = oracle.each_index(data)
+        for with_readinto in (False, True):
+            seen, err = [], None
+            try:
+                fin = fq.Parser(_ShortReader(data, with_readinto), engine=eng, chunk_bytes=chunk).each(
+                    lambda r: seen.append((r.offset, bytes(r.data), r.head(), r.seq(), r.qual())) or True)
+                assert fin is True
+            except fq.FastqError as e:
+                err = e
+            assert len(seen) == ores.n_records, (k, chunk)
+            assert (err.status if err else 0) == ores.status, (k, chunk)
+            if err:
+                assert err.offset == ores.err_offset and err.n_delivered == ores.n_records
+            for i, (_, raw, head, seq, qual) in enumerate(seen):
+                s, e0, e1, e2, e3 = (int(x) for x in oidx[i])
+                assert raw == data[s:e3 + 1]
+                assert head == data[s + 1:e0] and seq == data[e0 + 1:e1] and qual == data[e2 + 1:e3]
+        # record_sets / parallel_each over the same reader: same records (the batch holding the bad one is dropped)
+        n_sets = 0
+        try:
+            for s in fq.Parser(_ShortReader(data, True), engine=eng, chunk_bytes=chunk).record_sets():
+                n_sets += s.len()
+            assert ores.status == 0
+        except fq.FastqError as e:
+            assert e.status == ores.status
+        assert n_sets <= ores.n_records and (ores.status != 0 or n_sets == ores.n_records)
+
+
+def test_each_zipped_over_readers(fq, oracle, eng):
+    """src/lib.rs:577-609 over two readers consumed in refills of different sizes."""
+    a = oracle.synth_fixed_records(3000).tobytes()
+    b = oracle.synth_fixed_records(2500).tobytes()
+    pairs = []
+    fin = fq.each_zipped(fq.Parser(io.BytesIO(a), engine=eng, chunk_bytes=100000),
+                         fq.Parser(io.BytesIO(b), engine=eng, chunk_bytes=77777),
+                         lambda r1, r2: pairs.append((r1 is not None, r2 is not None)) or (True, True))
+    assert fin == (True, True)
+    assert sum(1 for p in pairs if p[0]) == 3000 and sum(1 for p in pairs if p[1]) == 2500
+    assert pairs[:2500] == [(True, True)] * 2500
+
+
 def test_fastq_count_example_on_a_10mb_file(fq, oracle, tmp_path):
     """BASELINE config 1 (examples/fastq-count.rs on a 10 MB synthetic 150 bp file: 31 152 records),
     through parse_path -> Parser.count() (reader thread -> pinned ring -> kernels) and through
