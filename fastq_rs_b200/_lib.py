@@ -16,6 +16,7 @@ ABI_VERSION = 2
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
 E_ARG, E_STATE, E_NOMEM, E_CUDA = 50, 51, 52, 100
+KEEP_ALL, KEEP_DNA, KEEP_DNAN = 0, 1, 2
 F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START, F_PARTIAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 MAX_RECORD_BYTES = 68 * 1024
 SYNTH_SEED = 0xFA57A11CE5EED001
@@ -29,7 +30,7 @@ SYMBOLS = [
     "fqb_device_stats", "fqb_device_result", "fqb_launch_count", "fqb_last_scan_ms", "fqb_parse_host",
     "fqb_stream_begin", "fqb_stream_acquire", "fqb_stream_submit", "fqb_stream_finish",
     "fqb_host_alloc", "fqb_host_free", "fqb_synth_fixed_device", "fqb_synth_var_device",
-    "fqb_synth_var_sizes_device",
+    "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter",
 ]
 
 
@@ -54,7 +55,7 @@ class Result(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("fq_scan.cu", "fq_stream.cu", "fq_kernels.cu", "fq_api.cu", "fq_common.cuh", "fq_device.cuh", "fq_hist.cuh")]
+    srcs = [os.path.join(src_dir, f) for f in ("fq_scan.cu", "fq_stream.cu", "fq_kernels.cu", "fq_filter.cu", "fq_api.cu", "fq_common.cuh", "fq_device.cuh", "fq_hist.cuh")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "fastq_b200.h"))
     stale = (not os.path.exists(SO_PATH)) or any(
         os.path.getmtime(p) > os.path.getmtime(SO_PATH) for p in srcs if os.path.exists(p))
@@ -127,6 +128,10 @@ def lib():
     L.fqb_synth_var_device.restype = i32
     L.fqb_synth_var_sizes_device.argtypes = [vp, u64, u64, u64, vp]
     L.fqb_synth_var_sizes_device.restype = i32
+    L.fqb_filter_device.argtypes = [vp, vp, u64, vp, u64, u64, u32, vp, u64, vp]
+    L.fqb_filter_device.restype = i32
+    L.fqb_fetch_filter.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64)]
+    L.fqb_fetch_filter.restype = i32
     if L.fqb_abi_version() != ABI_VERSION:
         raise RuntimeError("libfastq_b200.so ABI version mismatch")
     _lib = L

@@ -68,6 +68,12 @@ struct fqb_ctx {
     uint32_t* d_index_stage = nullptr;  // speculative launch: per-range staging of the line ends
     size_t index_stage_cap = 0;
     unsigned long long* d_linecount = nullptr;
+    // record filter workspace (grown on demand)
+    uint32_t* d_fkeep = nullptr;
+    unsigned long long* d_fblk = nullptr;
+    size_t fkeep_cap = 0, fblk_cap = 0;
+    unsigned long long* d_fmisc = nullptr;   // wraps [1 + FILTER_MAX_WRAPS] then result [4]
+    unsigned long long* h_fres = nullptr;    // pinned [4]
     DevResult* h_res = nullptr;  // pinned
     unsigned long long* h_linecount = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -238,6 +244,10 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_index_stage);
     cudaFree(ctx->d_linecount);
     cudaFree(ctx->d_carry);
+    cudaFree(ctx->d_fkeep);
+    cudaFree(ctx->d_fblk);
+    cudaFree(ctx->d_fmisc);
+    if (ctx->h_fres) cudaFreeHost(ctx->h_fres);
     cudaFree(ctx->d_trace);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->h_linecount) cudaFreeHost(ctx->h_linecount);
@@ -442,6 +452,67 @@ int fqb_fetch_line_count(fqb_ctx* ctx, void* stream, uint64_t* n_lines)
     CK(cudaMemcpyAsync(ctx->h_linecount, ctx->d_linecount, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *n_lines = *ctx->h_linecount;
+    return FQB_OK;
+}
+
+int fqb_filter_device(fqb_ctx* ctx, const uint8_t* d_bytes, uint64_t stream_offset, const uint32_t* d_index,
+                      uint64_t n_records, uint64_t first_offset, uint32_t mode, uint8_t* d_out, uint64_t out_cap,
+                      void* stream)
+{
+    if (!ctx || mode > FQB_KEEP_DNAN || first_offset < stream_offset) return FQB_E_ARG;
+    if (n_records && (!d_bytes || !d_index || (reinterpret_cast<uintptr_t>(d_bytes) & 15) ||
+                      (reinterpret_cast<uintptr_t>(d_index) & 3) || (out_cap && !d_out)))
+        return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    const size_t nblk = (size_t)((n_records + 255) / 256);
+    if (!ctx->d_fmisc) {
+        CK(cudaMalloc(&ctx->d_fmisc, (1 + FILTER_MAX_WRAPS + 4) * 8));
+        CK(cudaHostAlloc(&ctx->h_fres, 4 * 8, cudaHostAllocDefault));
+    }
+    if (n_records > ctx->fkeep_cap) {   // the previous call may still be running on another stream: wait for it
+        CK(cudaDeviceSynchronize());
+        cudaFree(ctx->d_fkeep);
+        ctx->d_fkeep = nullptr;
+        ctx->fkeep_cap = 0;
+        CK(cudaMalloc(&ctx->d_fkeep, (size_t)n_records * 4));
+        ctx->fkeep_cap = n_records;
+    }
+    if (nblk > ctx->fblk_cap) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(ctx->d_fblk);
+        ctx->d_fblk = nullptr;
+        ctx->fblk_cap = 0;
+        CK(cudaMalloc(&ctx->d_fblk, nblk * 16));
+        ctx->fblk_cap = nblk;
+    }
+    FilterParams p;
+    p.data = d_bytes;
+    p.index = d_index;
+    p.n_records = n_records;
+    p.stream_offset = stream_offset;
+    p.first_offset = first_offset;
+    p.mode = mode;
+    p.keep = ctx->d_fkeep;
+    p.blk = ctx->d_fblk;
+    p.wraps = ctx->d_fmisc;
+    p.out = d_out;
+    p.out_cap = out_cap;
+    p.result = ctx->d_fmisc + 1 + FILTER_MAX_WRAPS;
+    CK(launch_filter(p, ctx->num_sms, st));
+    ctx->launches += filter_launches(n_records);
+    return FQB_OK;
+}
+
+int fqb_fetch_filter(fqb_ctx* ctx, void* stream, uint64_t* n_kept, uint64_t* out_bytes)
+{
+    if (!ctx || !n_kept || !out_bytes || !ctx->d_fmisc) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(ctx->h_fres, ctx->d_fmisc + 1 + FILTER_MAX_WRAPS, 4 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_kept = ctx->h_fres[0];
+    *out_bytes = ctx->h_fres[1];
+    if (ctx->h_fres[2] > FILTER_MAX_WRAPS) return FQB_E_ARG;   // not an index of increasing offsets
     return FQB_OK;
 }
 

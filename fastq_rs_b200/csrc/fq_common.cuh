@@ -100,6 +100,25 @@ __host__ __device__ inline size_t stats_base_off(uint32_t P) { return 8 + (size_
 __host__ __device__ inline size_t stats_qual_off(uint32_t P) { return 8 + (size_t)P + 2 + 6 * (size_t)P; }
 __host__ __device__ inline size_t stats_words(uint32_t P) { return 8 + (size_t)P + 2 + 6 * (size_t)P + 256 * (size_t)P; }
 
+// record filter (fq_filter.cu)
+constexpr unsigned long long FILTER_MAX_WRAPS = 64;   // 32-bit offset wraps per call = 256 GiB of input
+struct FilterParams {
+    const uint8_t* data;               // shard bytes
+    const uint32_t* index;             // 4 line ends per record (low 32 bits of stream offsets)
+    unsigned long long n_records;
+    unsigned long long stream_offset;  // stream offset of data[0]
+    unsigned long long first_offset;   // stream offset of the first byte of record 0
+    uint32_t mode;                     // 0 keep all, 1 validate_dna, 2 validate_dnan
+    uint32_t* keep;                    // [n_records] record bytes if kept, else 0
+    unsigned long long* blk;           // [2 * blocks] kept bytes (-> exclusive prefix), kept records
+    unsigned long long* wraps;         // [0] count, [1..] records at which the 32-bit offsets wrap
+    uint8_t* out;
+    unsigned long long out_cap;
+    unsigned long long* result;        // [0] records kept [1] bytes kept [2] wraps seen
+};
+cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t st);
+int filter_launches(unsigned long long n_records);
+
 // launchers (fq_kernels.cu)
 size_t scan_smem_bytes(int nchunk);
 uint32_t scan_tile_bytes(int nchunk);

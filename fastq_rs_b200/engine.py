@@ -178,6 +178,25 @@ class Engine:
                                                        self._stream_ptr(stream)),
                "fqb_count_lines_device")
 
+    # ---- record filter (validate_dna / validate_dnan + Record::write) ------------------------
+    def filter_device(self, d_bytes, index, n_records: int, mode: int, out, *, stream_offset: int = 0,
+                      first_offset: int | None = None, stream=None) -> None:
+        """Enqueue: write the records of a parsed shard whose seq() passes the predicate (mode:
+        _lib.KEEP_ALL / KEEP_DNA / KEEP_DNAN, src/records.rs:19-33) verbatim into the uint8 CUDA tensor
+        `out`, densely, in order.  `index` = the int32 line-end index parse_device filled."""
+        first = stream_offset if first_offset is None else first_offset
+        _check(self.ctx, self.L.fqb_filter_device(
+            self.ctx, d_bytes.data_ptr(), stream_offset, index.data_ptr(), n_records, first, mode,
+            out.data_ptr() if out is not None else None, out.numel() if out is not None else 0,
+            self._stream_ptr(stream)), "fqb_filter_device")
+
+    def fetch_filter(self, stream=None) -> tuple[int, int]:
+        """(records kept, bytes they occupy) of the last filter_device (waits for it)."""
+        nk, nb = C.c_uint64(), C.c_uint64()
+        _check(self.ctx, self.L.fqb_fetch_filter(self.ctx, self._stream_ptr(stream), C.byref(nk), C.byref(nb)),
+               "fqb_fetch_filter")
+        return nk.value, nb.value
+
     def last_scan_ms(self) -> float:
         return float(self.L.fqb_last_scan_ms(self.ctx))
 

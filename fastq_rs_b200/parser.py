@@ -378,6 +378,31 @@ class Parser:
         return self._stream(hist=True)
 
 
+    def filter_to(self, writer, keep: str = "dnan") -> int:
+        """Write the records whose seq() passes validate_dna ("dna") / validate_dnan ("dnan") -- or
+        every record ("all") -- to `writer`, verbatim (Record::write, src/records.rs:93-96) and in
+        order; predicate and compaction run on the GPU.  Returns the number of records written;
+        raises FastqError after the records in front of a bad one have been written (each()'s order)."""
+        import torch
+        from ._lib import KEEP_ALL, KEEP_DNA, KEEP_DNAN
+        mode = {"all": KEEP_ALL, "dna": KEEP_DNA, "dnan": KEEP_DNAN}[keep]
+        eng = self._engine
+        data = _read_all(self._reader)
+        dev = f"cuda:{eng.device}"
+        d = torch.zeros(data.size + 64, dtype=torch.uint8, device=dev)
+        if data.size:
+            d[:data.size] = torch.from_numpy(data if data.flags.writeable else data.copy())
+        idx = torch.empty(data.size + 8, dtype=torch.int32, device=dev)
+        eng.parse_device(d, n_own=data.size, n_avail=data.size, hist=False, index=idx)
+        outcome, _ = eng.fetch(want_stats=False)
+        out = torch.empty(max(data.size, 1), dtype=torch.uint8, device=dev)
+        eng.filter_device(d, idx, outcome.n_records, mode, out)
+        n_kept, n_bytes = eng.fetch_filter()
+        writer.write(out[:n_bytes].cpu().numpy().tobytes())
+        outcome.raise_for_status()
+        return n_kept
+
+
 def each_zipped(parser1: Parser, parser2: Parser, callback) -> tuple[bool, bool]:
     """src/lib.rs:577-609, lock-step over two delimited streams."""
     it1, it2 = parser1.ref_iter(), parser2.ref_iter()

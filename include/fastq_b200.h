@@ -163,6 +163,24 @@ uint64_t fqb_launch_count(fqb_ctx *ctx);
  * (waits for it); <0 on error */
 float fqb_last_scan_ms(fqb_ctx *ctx);
 
+/* ---- record filter: the step after the path (validate_dna / validate_dnan + Record::write) --------
+ * Keeps the records whose seq() passes the predicate and writes their raw bytes ('@' .. final '\n',
+ * RefRecord::write, src/records.rs:93-96) to d_out densely and in stream order.
+ *   d_bytes / stream_offset : the shard that was parsed (same pointer and stream_offset)
+ *   d_index / n_records     : the line-end index fqb_parse_device wrote, starting at the first line end
+ *                             of record 0, and the number of records to consider (fqb_result.n_records)
+ *   first_offset            : stream offset of the first byte of record 0 (= stream_offset for a shard
+ *                             that starts at a record start)
+ * Asynchronous on `stream`; fqb_fetch_filter waits and returns the totals.  Records that do not fit in
+ * out_cap are not written (out_bytes > out_cap tells). */
+#define FQB_KEEP_ALL  0u
+#define FQB_KEEP_DNA  1u /* Record::validate_dna,  src/records.rs:19-23: seq() only A C T G       */
+#define FQB_KEEP_DNAN 2u /* Record::validate_dnan, src/records.rs:29-33: seq() only A C T G N     */
+int fqb_filter_device(fqb_ctx *ctx, const uint8_t *d_bytes, uint64_t stream_offset, const uint32_t *d_index,
+                      uint64_t n_records, uint64_t first_offset, uint32_t mode, uint8_t *d_out,
+                      uint64_t out_cap, void *stream);
+int fqb_fetch_filter(fqb_ctx *ctx, void *stream, uint64_t *n_kept, uint64_t *out_bytes);
+
 /* ---- host path: bytes in host memory, staged through the pinned ring --------------------
  * replaces Parser::new(reader).each(stats closure) end to end.  Synchronous.
  * host_index (optional): receives the low 32 bits of the stream offset of every '\n'

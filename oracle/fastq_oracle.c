@@ -421,6 +421,38 @@ void fqo_each_index(const uint8_t *data, size_t len, size_t bufsize, size_t max_
     fqo_each(&rd, bufsize, index_cb, &k, res);
 }
 
+/* each() with a closure that writes the records passing validate_dna (mode 1) / validate_dnan (mode 2)
+ * (src/records.rs:19-33; mode 0 = every record) with RefRecord::write (src/records.rs:93-96: raw bytes) */
+typedef struct {
+    uint8_t *out;
+    size_t cap, n_bytes, n_kept;
+    int mode;
+} filter_sink;
+
+static int filter_cb(void *user, const fqo_ref_record *rec, uint64_t off)
+{
+    filter_sink *k = (filter_sink *)user;
+    (void)off;
+    int ok = k->mode == 1 ? fqo_validate_dna(rec) : k->mode == 2 ? fqo_validate_dnan(rec) : 1;
+    if (ok) {
+        if (k->n_bytes + rec->len <= k->cap)
+            memcpy(k->out + k->n_bytes, rec->data, rec->len);
+        k->n_bytes += rec->len;
+        k->n_kept++;
+    }
+    return 1;
+}
+
+void fqo_each_filter(const uint8_t *data, size_t len, size_t bufsize, size_t max_read, int mode,
+                     uint8_t *out, size_t cap, uint64_t *n_kept, uint64_t *n_bytes, fqo_each_result *res)
+{
+    fqo_reader rd = {data, len, 0, max_read};
+    filter_sink k = {out, cap, 0, 0, mode};
+    fqo_each(&rd, bufsize, filter_cb, &k, res);
+    *n_kept = k.n_kept;
+    *n_bytes = k.n_bytes;
+}
+
 /* ======================================================================================
  * record_sets (src/lib.rs:355-436)
  * ==================================================================================== */

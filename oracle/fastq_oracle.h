@@ -120,6 +120,10 @@ void fqo_each_stats(const uint8_t *data, size_t len, size_t bufsize, size_t max_
 /* each() collecting the absolute offsets of every delivered record:
  * out[5*i+0..4] = record start, head '\n', seq '\n', sep '\n', qual '\n' (stream offsets).
  * At most cap records are stored; res->n_delivered is always the true count. */
+/* each() + a closure writing the records that pass validate_dna (1) / validate_dnan (2) / all (0)
+ * verbatim (src/records.rs:19-33, 93-96) */
+void fqo_each_filter(const uint8_t *data, size_t len, size_t bufsize, size_t max_read, int mode,
+                     uint8_t *out, size_t cap, uint64_t *n_kept, uint64_t *n_bytes, fqo_each_result *res);
 void fqo_each_index(const uint8_t *data, size_t len, size_t bufsize, size_t max_read,
                     uint64_t *out, size_t cap, fqo_each_result *res);
 

@@ -92,6 +92,10 @@ def lib():
         L.fqo_each_index.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                      C.c_void_p, C.c_size_t, C.POINTER(_EachResult)]
         L.fqo_each_index.restype = None
+        L.fqo_each_filter.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
+                                      C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(_EachResult)]
+        L.fqo_each_filter.restype = None
         L.fqo_parallel_each_stats.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                               C.c_int, C.POINTER(_Stats), C.c_void_p]
         L.fqo_parallel_each_stats.restype = C.c_int
@@ -272,6 +276,20 @@ def each_index(data, bufsize: int = BUFSIZE, max_read: int = 0, cap: int | None 
                      C.byref(res))
     n = min(cap, res.n_delivered)
     return EachResult(res.status, bool(res.finished), res.n_delivered, res.err_offset), out[:n]
+
+
+def each_filter(data, mode: int, bufsize: int = BUFSIZE, max_read: int = 0):
+    """each() with a closure that writes the records passing validate_dna (mode 1) / validate_dnan
+    (mode 2) / every record (mode 0) verbatim.  Returns (EachResult, n_kept, bytes written)."""
+    L = lib()
+    a = _as_u8(data)
+    out = np.empty(max(a.size, 1), dtype=np.uint8)
+    res = _EachResult()
+    nk, nb = C.c_uint64(0), C.c_uint64(0)
+    L.fqo_each_filter(a.ctypes.data, a.size, bufsize, max_read, mode, out.ctypes.data, out.size,
+                      C.byref(nk), C.byref(nb), C.byref(res))
+    return (EachResult(res.status, bool(res.finished), res.n_delivered, res.err_offset), nk.value,
+            out[:nb.value].tobytes())
 
 
 def parallel_each_stats(data, max_len: int, n_threads: int, bufsize: int = BUFSIZE,

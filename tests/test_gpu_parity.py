@@ -727,6 +727,95 @@ def test_each_zipped_over_readers(fq, oracle, eng):
     assert pairs[:2500] == [(True, True)] * 2500
 
 
+# --------------------------------------------------------------------------------------------
+# record filter: validate_dna / validate_dnan as GPU predicates + compaction
+# --------------------------------------------------------------------------------------------
+def _filter_cases(oracle):
+    rng = np.random.default_rng(7)
+    recs = []
+    for i in range(3000):
+        L = int(rng.integers(0, 200))
+        r = bytearray(_rec(i, L, crlf=(i % 11 == 0)))
+        if L and i % 3 == 0:      # plant a byte outside the alphabets somewhere in the record
+            pos = int(rng.integers(0, len(r)))
+            if r[pos] not in b"\r\n@+":
+                r[pos] = int(rng.choice(np.frombuffer(b"acgtnXN.RYKM\x00\xff", dtype=np.uint8)))
+        recs.append(bytes(r))
+    mixed = b"".join(recs)
+    return {
+        "mixed": mixed,
+        "synthetic_fixed": oracle.synth_fixed_records(5000).tobytes(),
+        "synthetic_var": oracle.synth_var(3000).tobytes(),
+        "empty": b"",
+        "one_empty_seq": b"@id\n\n+\n\n",
+        "lone_cr_seq": b"@a\n\r\n+\n\r\n@b\nAC\r\n+\n!!\r\n",
+        "error_behind": mixed[:20000] + b"\nGARBAGE",
+        "truncated": mixed[:-3],
+        "long": b"".join(_rec(i, L) for i, L in enumerate([30000, 5, 33000, 0, 1, 2, 3, 4, 150])),
+    }
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_filter_device(mode, fq, torch, oracle, eng):
+    for name, data in _filter_cases(oracle).items():
+        ores, n_kept, want = oracle.each_filter(data, mode)
+        d = to_dev(torch, data)
+        idx = torch.zeros(len(data) + 8, dtype=torch.int32, device="cuda")
+        eng.parse_device(d, n_own=len(data), n_avail=len(data), hist=False, index=idx)
+        out, _ = eng.fetch(want_stats=False)
+        assert (out.status, out.n_records) == (ores.status, ores.n_records), name
+        dst = torch.full((len(data) + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+        eng.filter_device(d, idx, out.n_records, mode, dst)
+        got_n, got_b = eng.fetch_filter()
+        assert (got_n, got_b) == (n_kept, len(want)), name
+        h = dst.cpu().numpy()
+        assert h[:got_b].tobytes() == want, name
+        assert (h[got_b:] == 0xEE).all(), name           # nothing written behind the output
+        # an output buffer that is too small: totals still reported, nothing written behind its end
+        if got_b > 100:
+            small = torch.full((got_b // 2 + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+            eng.filter_device(d, idx, out.n_records, mode, small[:got_b // 2])
+            assert eng.fetch_filter() == (n_kept, len(want))
+            hs = small.cpu().numpy()
+            cap = got_b // 2
+            assert (hs[cap:] == 0xEE).all()
+            neq = np.nonzero(hs[:cap] != np.frombuffer(want[:cap], dtype=np.uint8))[0]
+            x = int(neq[0]) if neq.size else cap          # whole records only: the rest stays untouched
+            assert (hs[x:cap] == 0xEE).all() and cap - x < 69632
+
+
+def test_filter_nonzero_stream_offset_and_wrap(fq, torch, oracle, eng):
+    """Index entries are the low 32 bits of stream offsets: a shard whose offsets cross a 4 GiB
+    boundary filters exactly like the same bytes at offset 0."""
+    data = oracle.synth_fixed_records(4000).tobytes()
+    _, n_kept, want = oracle.each_filter(data, 1)
+    d = to_dev(torch, data)
+    for off in (0, (1 << 32) - 321 * 1000 - 7, (5 << 32) - 100, (1 << 40) + 12345):
+        idx = torch.zeros(len(data) + 8, dtype=torch.int32, device="cuda")
+        eng.parse_device(d, n_own=len(data), n_avail=len(data), hist=False, index=idx, stream_offset=off)
+        out, _ = eng.fetch(want_stats=False)
+        assert out.status == 0 and out.n_records == 4000
+        dst = torch.zeros(len(data), dtype=torch.uint8, device="cuda")
+        eng.filter_device(d, idx, out.n_records, fq._lib.KEEP_DNA, dst, stream_offset=off)
+        assert eng.fetch_filter() == (n_kept, len(want))
+        assert dst[:len(want)].cpu().numpy().tobytes() == want
+
+
+def test_parser_filter_to(fq, oracle, eng):
+    data = _filter_cases(oracle)["mixed"]
+    for keep, mode in (("all", 0), ("dna", 1), ("dnan", 2)):
+        _, n_kept, want = oracle.each_filter(data, mode)
+        w = io.BytesIO()
+        assert fq.Parser(data, engine=eng).filter_to(w, keep) == n_kept
+        assert w.getvalue() == want
+    bad = data[:20000] + b"\nGARBAGE"
+    _, n_kept, want = oracle.each_filter(bad, 2)
+    w = io.BytesIO()
+    with pytest.raises(fq.FastqError):
+        fq.Parser(bad, engine=eng).filter_to(w, "dnan")
+    assert w.getvalue() == want
+
+
 def test_fastq_count_example_on_a_10mb_file(fq, oracle, tmp_path):
     """BASELINE config 1 (examples/fastq-count.rs on a 10 MB synthetic 150 bp file: 31 152 records),
     through parse_path -> Parser.count() (reader thread -> pinned ring -> kernels) and through
