@@ -135,6 +135,28 @@ def test_validate_dna():
                                                            (False, False)]
 
 
+def test_each_filter_matches_the_python_model():
+    """fqo_each_filter = each() + `if rec.validate_dna(n)() { rec.write(w) }` (src/records.rs:19-33, 93-96),
+    checked against the independent pure-Python model of each() with the predicate spelled out."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(400):
+        L = int(rng.integers(0, 40))
+        alpha = b"ACGT" if i % 3 else (b"ACGTN" if i % 2 else b"ACGTNacgtX.")
+        seq = bytes(rng.choice(np.frombuffer(alpha, dtype=np.uint8), L))
+        e = b"\r\n" if i % 7 == 0 else b"\n"
+        recs.append(b"@r%d" % i + e + seq + e + b"+" + e + b"I" * L + e)
+    for data in (b"".join(recs), b"".join(recs) + b"@x\nAC", b"", b"@a\n\n+\n\n", b"".join(recs[:50]) + b"junk\n"):
+        status, model = pymodel.each(data)
+        for mode, alphabet in ((0, None), (1, b"ACTG"), (2, b"ACTGN")):
+            keep = [r for r in model if alphabet is None or all(c in alphabet for c in r[1])]
+            res, n_kept, out = oracle.each_filter(data, mode)
+            assert res.status == status and res.n_records == len(model)
+            assert n_kept == len(keep)
+            assert out == b"".join(r[3] for r in keep)
+
+
 def test_each_stop_early():
     data = b"@a\nA\n+\n!\n" * 5
     seen = []
