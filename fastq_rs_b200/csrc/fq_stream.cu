@@ -416,6 +416,38 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     return first_bad;
 }
 
+// Same for records whose HEADER length varies (instrument coordinates in the id line): lane r holds the
+// window offset of record r and its header length (found by the caller's search for the first '\n' behind the
+// record start, so the header line needs no further check); everything behind the header is predicted from
+// the shape and verified as in pred_pass.  chk_rel: the byte lane i verifies, relative to the sequence line.
+template <class C>
+__device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, uint32_t my_start, uint32_t my_lh,
+                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t nq,
+                                              const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
+                                              uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
+{
+    const uint32_t r = 4u * pass + sub;
+    const bool valid = r < n_rec;
+    const uint32_t from = valid ? r : 0u;
+    const uint32_t s = buf_s + __shfl_sync(0xffffffffu, my_start, from);
+    const uint32_t body = s + __shfl_sync(0xffffffffu, my_lh, from);     // shared address of the sequence line
+    bool lane_ok = ((lds_u8(i == 0u ? s : body + chk_rel) == chk_exp) ? 1u : 0u) != chk_neg;
+    if (sh.Lp > 2u) lane_ok = lane_ok && no_newline32(body, sh.Lsq + 1u, sh.Lsq + sh.Lp - 1u, i, kA, kB);
+    const unsigned nok = __ballot_sync(0xffffffffu, valid && !lane_ok);
+    uint32_t first_bad = NO_START;
+    bool ok = valid;
+    if (nok) {
+        const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;
+        first_bad = 4u * pass + fsub;
+        ok = valid && sub < fsub;
+    }
+    const uint32_t sa = body + 4u * i;
+    const uint32_t qa = sa + sh.Lsq + sh.Lp;
+    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, max(ns, nq), min(ns, nq), ok ? 1u : 0u,
+                       ok ? 0x10000u : 0u, hist_s, lc, hib);
+    return first_bad;
+}
+
 // '\n' count of a full window at positions >= pad (no list, no ranks: ~1/3 of the scan)
 template <class C>
 __device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t pad, int lane, uint32_t kA, uint32_t kB)
@@ -562,7 +594,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         // per-lane constants of the shape (set with it): the byte this lane verifies in every record,
         // the line end this lane writes to the index, and how many records fit a window
         uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0;
-        bool predict = false;
+        bool predict = false, flex = false;   // flex: header lengths vary, see flex_pass
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
@@ -572,7 +604,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             uint32_t n_rec, n_lines, next;
             // ---- predicted window: full, inside the owned bytes, at least one record ------------------
             const uint32_t n_fit = nfit_max - (w.pad > nfit_rem ? 1u : 0u);   // = (WIN - pad) / reclen
-            const bool can_predict = predict && n_fit && w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own;
+            const bool full = w.vlen == (uint32_t)C::WIN && w.src + C::WIN <= (long long)p.n_own;
+            const bool can_predict = predict && !flex && n_fit && full;
             if (can_predict && !HIST) {
                 // ---- no histograms: the window holds n_fit predicted records and the head of the next.
                 // All their predicted line ends (and '@', '+') are verified byte by byte, and the window
@@ -659,6 +692,74 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
                     for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
                 }
+            } else if (HIST && predict && flex && full) {
+                // ---- predicted window, header lengths vary: find every header end ('\n' search over the 128
+                // bytes behind the record start), predict the rest of the record from the shape
+                const uint32_t rest = 2u * sh.Lsq + sh.Lp;
+                const uint32_t lim = room < (unsigned long long)C::WIN ? (uint32_t)room : (uint32_t)C::WIN;
+                uint32_t my_start = 0, my_lh = 0, s = w.pad, n_fit2 = 0;
+                while (n_fit2 < 16u && s < lim) {
+                    const uint32_t a0 = s & ~3u;
+                    uint32_t m = nlbits3(lds32<0>(buf_s + a0 + 4u * (uint32_t)lane), kA, kB);
+                    if (lane == 0) m &= 0xFFFFFFFFu << ((s & 3u) * 8u);          // bytes in front of the record
+                    const unsigned any = __ballot_sync(0xffffffffu, m != 0u);
+                    if (!any) break;                                             // header longer than the search
+                    const uint32_t f = (uint32_t)__ffs(any) - 1u;
+                    const uint32_t mf = __shfl_sync(0xffffffffu, m, f);
+                    const uint32_t lh = a0 + 4u * f + (((uint32_t)__ffs(mf) - 1u) >> 3) + 1u - s;
+                    const uint32_t e = s + lh + rest;
+                    if (e > (uint32_t)C::WIN) break;                             // the record does not fit the window
+                    if ((uint32_t)lane == n_fit2) {
+                        my_start = s;
+                        my_lh = lh;
+                    }
+                    ++n_fit2;
+                    s = e;
+                }
+                if (n_fit2 == 0) {
+                    predict = false;                                             // scan this window instead
+                    continue;
+                }
+                n_rec = n_fit2;
+                const uint32_t Lr = sh.Lsq - 1u;
+                const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;
+                uint32_t first_bad = NO_START, hib = 0;
+                for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
+                    first_bad = flex_pass<C>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, Ls, Lq, lc, hist_s, n_rec,
+                                             pass, sub, li, kA, kB, hib);
+                if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                    failed = true;
+                    break;
+                }
+                if (first_bad != NO_START) {
+                    n_rec = first_bad;
+                    predict = false;
+                    if (2u * first_bad < n_fit2 && ++strikes >= 2) cooldown = 32;
+                } else {
+                    strikes = 0;
+                }
+                ++dbg_pred;
+                if (n_rec == 0) continue;
+                if (lane == 0) {
+                    atomicAdd(&cta.n_records, n_rec);
+                    atomicAdd(&cta.n_bases, n_rec * Ls);
+                    atomicAdd(lenh + Ls, n_rec);
+                }
+                n_lines = 4u * n_rec;
+                const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 15u);
+                next = n_rec == n_fit2 ? s : nxt;
+                if (want_index) {
+                    if (lrank + n_lines > p.stage_share) {
+                        failed = true;
+                        break;
+                    }
+                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
+                    for (uint32_t b = 0; b < n_lines; b += 32u) {
+                        const uint32_t j = b + (uint32_t)lane, r = min(j >> 2, 15u);
+                        const uint32_t v = __shfl_sync(0xffffffffu, my_start, r) + __shfl_sync(0xffffffffu, my_lh, r);
+                        if (j < n_lines) out[j] = (uint32_t)(p.stream_offset + w.src) + v + idx_le;
+                    }
+                }
             } else {
                 // ---- scanned window -------------------------------------------------------------------
                 ++dbg_scan;
@@ -703,12 +804,31 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     sh.cr_s = (sh.Lsq > 1u && buf[l2 - 2u] == '\r') ? 1u : 0u;
                     sh.cr_q = (sh.Lsq > 1u && buf[l4 - 2u] == '\r') ? 1u : 0u;
                     if (cooldown) --cooldown;
+                    // do the records of this window (the first 32) share the shape?  Reads of varying length are
+                    // not predicted at all; headers of varying length are, with a search for every header end
+                    bool all_sq, all_h;
+                    {
+                        const uint32_t j = 4u * min((uint32_t)lane, n_win - 1u);
+                        const uint32_t a = list[j], b = list[j + 1u], c = list[j + 2u], d = list[j + 3u];
+                        all_sq = __all_sync(0xffffffffu, c - b == sh.Lsq && d - c == sh.Lp);
+                        all_h = __all_sync(0xffffffffu, b - a == sh.Lh);
+                    }
                     // with histograms: every byte of the sequence / quality lines must have a counter (the
                     // '\n' row is what checks them) and header / separator are checked 32 bytes at a time;
-                    // without: the '\n' count of the window checks every line, any shape will do
-                    predict = cooldown == 0 && sh.Lh >= 2u && sh.Lp >= 2u &&
-                              (HIST ? (sh.Lsq - 1u <= Pm && sh.Lh <= 64u && sh.Lp <= 34u) : true);
-                    if (predict) {
+                    // without: the '\n' count of the window checks every line
+                    flex = HIST && (!all_h || sh.Lh > 64u);
+                    predict = cooldown == 0 && sh.Lh >= 2u && sh.Lp >= 2u && all_sq &&
+                              (HIST ? (sh.Lsq - 1u <= Pm && sh.Lp <= 34u) : all_h);
+                    if (predict && flex) {
+                        const uint32_t rest = 2u * sh.Lsq + sh.Lp;
+                        // relative to the first byte of the sequence line (lane 0 looks at the record start)
+                        chk_off = li == 1 ? 0u - 1u : li == 2 ? sh.Lsq - 1u : li == 3 ? sh.Lsq : li == 4 ? sh.Lsq + sh.Lp - 1u
+                                : li == 5 ? rest - 1u : li == 6 ? sh.Lsq - 2u : rest - 2u;
+                        chk_exp = li == 0 ? '@' : li == 3 ? '+' : li >= 6 ? '\r' : '\n';
+                        chk_neg = (li == 6 && !sh.cr_s) || (li == 7 && !sh.cr_q) ? 1u : 0u;
+                        const uint32_t k = (uint32_t)lane & 3u;
+                        idx_le = k == 0 ? 0u - 1u : k == 1 ? sh.Lsq - 1u : k == 2 ? sh.Lsq + sh.Lp - 1u : rest - 1u;
+                    } else if (predict) {
                         const uint32_t o2 = sh.Lh + sh.Lsq;
                         // the byte lane li of a record's 8 lanes verifies (relative to the record start)
                         chk_off = li == 0 ? 0u : li == 1 ? sh.Lh - 1u : li == 2 ? o2 - 1u : li == 3 ? o2

@@ -361,6 +361,57 @@ def test_prediction_crlf_and_mixed_endings(torch, oracle, eng):
     check_device_vs_oracle(torch, oracle, eng, a + b + a)
 
 
+def _illumina(n, L=150, seed=0, crlf=False, sep_id=False, hdr_extra=0):
+    """fixed-length reads whose id lines vary in length (tile / x / y coordinates)"""
+    rng = np.random.default_rng(seed)
+    e = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(n):
+        h = b"@A00123:45:HXXXXDSXX:1:%d:%d:%d 1:N:0:ATCACGTT" % (rng.integers(1101, 2678), rng.integers(1, 30000),
+                                                                 rng.integers(1, 100000))
+        h += b"x" * int(rng.integers(0, hdr_extra + 1))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), L))
+        qual = bytes(rng.integers(33, 75, L, dtype=np.uint8))
+        out.append(h + e + seq + e + b"+" + (h[1:] if sep_id else b"") + e + qual + e)
+    return out
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "L100", "long_headers", "sep_id", "L0"])
+def test_prediction_varying_header_lengths(variant, torch, oracle, eng):
+    """Headers of varying length (real instrument ids): the kernel searches every header end and predicts
+    the rest of the record; result identical to the oracle, index included."""
+    recs = {"plain": lambda: _illumina(6000), "crlf": lambda: _illumina(6000, crlf=True),
+            "L100": lambda: _illumina(6000, L=100), "long_headers": lambda: _illumina(6000, hdr_extra=90),
+            "sep_id": lambda: _illumina(3000, L=60, sep_id=True), "L0": lambda: _illumina(3000, L=0)}[variant]()
+    check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
+
+
+@pytest.mark.parametrize("where", ["seq_nl", "qual_nl", "plus", "at", "short_read", "long_read", "header_200", "qual_short"])
+def test_varying_headers_with_a_bad_or_odd_record(where, torch, oracle, eng):
+    recs = _illumina(4000, seed=3)
+    k = 2777
+    r = bytearray(recs[k])
+    h = r.index(b"\n")
+    if where == "seq_nl":
+        r[h + 40] = 10
+    elif where == "qual_nl":
+        r[h + 1 + 151 + 2 + 70] = 10
+    elif where == "plus":
+        r[h + 1 + 151] = ord("-")
+    elif where == "at":
+        r[0] = ord("A")
+    elif where == "short_read":                       # a valid record with a shorter read: not an error
+        r = bytearray(_rec(k, 90))
+    elif where == "long_read":
+        r = bytearray(_rec(k, 151))
+    elif where == "header_200":                       # header longer than the search window: valid
+        r = bytearray(b"@" + b"h" * 200 + bytes(r[h:]))
+    elif where == "qual_short":                       # length mismatch
+        del r[-2]
+    recs[k] = bytes(r)
+    check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
+
+
 @pytest.mark.parametrize("where", ["seq", "qual", "header", "sep"])
 def test_prediction_stray_newline(where, torch, oracle, eng):
     """A '\n' inside a line of a record deep inside a predicted run: all predicted line ends are
