@@ -499,7 +499,8 @@ def test_count_mode_varying_shapes(torch, oracle, eng):
 
 @pytest.mark.parametrize("seed", list(range(12)))
 def test_prediction_fuzz(seed, torch, oracle, eng, eng300):
-    """Runs of records with a constant shape (what the predicting delimiter feeds on) glued together
+    """Runs of records with a constant shape (what the predicting delimiter feeds on) -- or a constant
+    shape but for the length of the id line -- glued together
     with shape changes, CRLF blocks, text after '+', and -- in two thirds of the seeds -- one
     anomaly somewhere: the GPU result must equal the oracle's in histogram mode and in count mode."""
     rng = np.random.default_rng(1000 + seed)
@@ -512,8 +513,9 @@ def test_prediction_fuzz(seed, torch, oracle, eng, eng300):
         hl = int(rng.integers(1, 70))
         eol = b"\r\n" if rng.random() < 0.2 else b"\n"
         sep_txt = bytes(rng.integers(65, 91, size=int(rng.integers(0, 40))).astype(np.uint8)) if rng.random() < 0.2 else b""
+        jitter = int(rng.choice([0, 0, 3, 8, 100]))               # id lines of varying length inside a run
         for _ in range(run):
-            head = (b"%d" % i).ljust(hl, b"x")[:max(hl, 1)]
+            head = (b"%d" % i).ljust(hl, b"x")[:max(hl, 1)] + b"y" * int(rng.integers(0, jitter + 1))
             seq = bytes(b"ACGTN"[int(x)] for x in rng.integers(0, 5, size=L))
             qual = bytes(rng.integers(33, 75, size=L).astype(np.uint8))
             recs.append(b"@" + head + eol + seq + eol + b"+" + sep_txt + eol + qual + eol)
