@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t rest = 2u * sh.Lsq + sh.Lp;
                 const uint32_t lim = room < (unsigned long long)C::WIN ? (uint32_t)room : (uint32_t)C::WIN;
                 uint32_t my_start = 0, my_lh = 0, s = w.pad, n_fit2 = 0;
-                while (n_fit2 < 16u && s < lim) {
+                while (n_fit2 < 32u && s < lim) {
                     const uint32_t a0 = s & ~3u;
                     uint32_t m = nlbits3(lds32<0>(buf_s + a0 + 4u * (uint32_t)lane), kA, kB);
                     if (lane == 0) m &= 0xFFFFFFFFu << ((s & 3u) * 8u);          // bytes in front of the record
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     atomicAdd(lenh + Ls, n_rec);
                 }
                 n_lines = 4u * n_rec;
-                const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 15u);
+                const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 31u);
                 next = n_rec == n_fit2 ? s : nxt;
                 if (want_index) {
                     if (lrank + n_lines > p.stage_share) {
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     }
                     uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
                     for (uint32_t b = 0; b < n_lines; b += 32u) {
-                        const uint32_t j = b + (uint32_t)lane, r = min(j >> 2, 15u);
+                        const uint32_t j = b + (uint32_t)lane, r = min(j >> 2, 31u);
                         const uint32_t v = __shfl_sync(0xffffffffu, my_start, r) + __shfl_sync(0xffffffffu, my_lh, r);
                         if (j < n_lines) out[j] = (uint32_t)(p.stream_offset + w.src) + v + idx_le;
                     }
@@ -815,7 +815,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     }
                     // with histograms: every byte of the sequence / quality lines must have a counter (the
                     // '\n' row is what checks them) and header / separator are checked 32 bytes at a time;
-                    // without: the '\n' count of the window checks every line
+                    // without: the '\n' count of the window checks every line (a per-record header search was
+                    // measured there too: 3.2 TB/s against the 3.8 TB/s of simply scanning, so it is not used)
                     flex = HIST && (!all_h || sh.Lh > 64u);
                     predict = cooldown == 0 && sh.Lh >= 2u && sh.Lp >= 2u && all_sq &&
                               (HIST ? (sh.Lsq - 1u <= Pm && sh.Lp <= 34u) : all_h);

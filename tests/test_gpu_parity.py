@@ -376,13 +376,14 @@ def _illumina(n, L=150, seed=0, crlf=False, sep_id=False, hdr_extra=0):
     return out
 
 
-@pytest.mark.parametrize("variant", ["plain", "crlf", "L100", "long_headers", "sep_id", "L0"])
+@pytest.mark.parametrize("variant", ["plain", "crlf", "L100", "long_headers", "sep_id", "L0", "L25"])
 def test_prediction_varying_header_lengths(variant, torch, oracle, eng):
     """Headers of varying length (real instrument ids): the kernel searches every header end and predicts
     the rest of the record; result identical to the oracle, index included."""
     recs = {"plain": lambda: _illumina(6000), "crlf": lambda: _illumina(6000, crlf=True),
             "L100": lambda: _illumina(6000, L=100), "long_headers": lambda: _illumina(6000, hdr_extra=90),
-            "sep_id": lambda: _illumina(3000, L=60, sep_id=True), "L0": lambda: _illumina(3000, L=0)}[variant]()
+            "sep_id": lambda: _illumina(3000, L=60, sep_id=True), "L0": lambda: _illumina(3000, L=0),
+            "L25": lambda: _illumina(9000, L=25)}[variant]()   # more than 32 records per window
     check_device_vs_oracle(torch, oracle, eng, b"".join(recs))
 
 
