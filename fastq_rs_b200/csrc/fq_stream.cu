@@ -287,6 +287,46 @@ struct SRounds<C, C::NCHUNK> {
     }
 };
 
+// The same rounds for records of a predicted shape with seq() and qual() of one length n: only the last round
+// is partial, and which of a lane's four bumps of that round lie inside the line is the same for every record
+// of the shape -- byte k of gm is 1 where the k-th bump counts (0 for lanes without a record), so the guard is
+// one PRMT per bump instead of a compare and a select.
+template <class C, int T>
+struct FRounds {
+    static __device__ __forceinline__ void run(uint32_t as0, uint32_t aq0, uint32_t shs, uint32_t shq, uint32_t n,
+                                               uint32_t inc_s, uint32_t inc_q, uint32_t gm, const LaneK& lc, uint32_t& hib)
+    {
+        if (32u * T >= n) return;                                         // warp-uniform
+        const uint32_t s0 = lds32<32 * T>(as0), s1 = lds32<32 * T + 4>(as0);
+        const uint32_t q0 = lds32<32 * T>(aq0), q1 = lds32<32 * T + 4>(aq0);
+        const uint32_t vs = __funnelshift_r(s0, s1, shs);
+        const uint32_t vq = __funnelshift_r(q0, q1, shq);
+        hib |= vs | vq;
+        constexpr int CO = 4 * C::CHUNK_WORDS * T;
+        if (32u * (T + 1) <= n) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), inc_s);
+                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), inc_q);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), __byte_perm(gm, 0u, 0x4440u + (uint32_t)k));
+                red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), __byte_perm(gm, 0u, 0x4044u + ((uint32_t)k << 8)));
+            }
+        }
+        FRounds<C, T + 1>::run(as0, aq0, shs, shq, n, inc_s, inc_q, gm, lc, hib);
+    }
+};
+template <class C>
+struct FRounds<C, C::NCHUNK> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                                               uint32_t, const LaneK&, uint32_t&)
+    {
+    }
+};
+
 // bytes [from, to) of the window (to - from <= 32) hold no '\n': lane i of the 8-lane group looks at
 // the 4 bytes from + 4i .. (two aligned words, funnel shift); lane-local answer, the caller votes
 __device__ __forceinline__ bool no_newline32(uint32_t buf_s, uint32_t from, uint32_t to, uint32_t i, uint32_t kA, uint32_t kB)
@@ -384,7 +424,7 @@ struct Shape {
 
 template <class C>
 __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, uint32_t pad, uint32_t chk_off,
-                                              uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t nq,
+                                              uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t gm,
                                               const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
                                               uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
 {
@@ -411,8 +451,7 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     // window buffers), so nothing faults; the caller raises spec_fail and the exact path redoes the shard.
     // (ns, nq are the same for every record of the window: the guards of the last, partial round do
     // not depend on the pass, only the increments do)
-    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, max(ns, nq), min(ns, nq), ok ? 1u : 0u,
-                       ok ? 0x10000u : 0u, hist_s, lc, hib);
+    FRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
     return first_bad;
 }
 
@@ -422,7 +461,7 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
 // the shape and verified as in pred_pass.  chk_rel: the byte lane i verifies, relative to the sequence line.
 template <class C>
 __device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, uint32_t my_start, uint32_t my_lh,
-                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t nq,
+                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t gm,
                                               const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
                                               uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
 {
@@ -443,8 +482,7 @@ __device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, u
     }
     const uint32_t sa = body + 4u * i;
     const uint32_t qa = sa + sh.Lsq + sh.Lp;
-    SRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, nq, max(ns, nq), min(ns, nq), ok ? 1u : 0u,
-                       ok ? 0x10000u : 0u, hist_s, lc, hib);
+    FRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
     return first_bad;
 }
 
@@ -593,7 +631,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         Shape sh = {0, 0, 0, 0, 0, 1};
         // per-lane constants of the shape (set with it): the byte this lane verifies in every record,
         // the line end this lane writes to the index, and how many records fit a window
-        uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0;
+        uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0, gmask = 0;
         bool predict = false, flex = false;   // flex: header lengths vary, see flex_pass
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
@@ -654,10 +692,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 n_rec = n_fit;
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
                 const uint32_t Lr = sh.Lsq - 1u;
-                const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;       // seq()/qual() drop one trailing '\r'
+                const uint32_t Ls = Lr - sh.cr_s;                           // seq()/qual() drop one trailing '\r' (cr_s == cr_q)
                 uint32_t first_bad = NO_START, hib = 0;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = pred_pass<C>(buf_s, sh, w.pad, chk_off, chk_exp, chk_neg, Ls, Lq, lc, hist_s, n_rec, pass,
+                    first_bad = pred_pass<C>(buf_s, sh, w.pad, chk_off, chk_exp, chk_neg, Ls, gmask, lc, hist_s, n_rec, pass,
                                              sub, li, kA, kB, hib);
                 if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;   // bytes >= 0x80 reached the rounds: the exact path
@@ -722,10 +760,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 }
                 n_rec = n_fit2;
                 const uint32_t Lr = sh.Lsq - 1u;
-                const uint32_t Ls = Lr - sh.cr_s, Lq = Lr - sh.cr_q;
+                const uint32_t Ls = Lr - sh.cr_s;
                 uint32_t first_bad = NO_START, hib = 0;
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = flex_pass<C>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, Ls, Lq, lc, hist_s, n_rec,
+                    first_bad = flex_pass<C>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, Ls, gmask, lc, hist_s, n_rec,
                                              pass, sub, li, kA, kB, hib);
                 if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;
@@ -819,7 +857,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     // measured there too: 3.2 TB/s against the 3.8 TB/s of simply scanning, so it is not used)
                     flex = HIST && (!all_h || sh.Lh > 64u);
                     predict = cooldown == 0 && sh.Lh >= 2u && sh.Lp >= 2u && all_sq &&
-                              (HIST ? (sh.Lsq - 1u <= Pm && sh.Lp <= 34u) : all_h);
+                              (HIST ? (sh.Lsq - 1u <= Pm && sh.Lp <= 34u && sh.cr_s == sh.cr_q) : all_h);
+                    if (HIST && predict) {
+                        // which bumps of the last, partial round lie inside seq() / qual() (see FRounds)
+                        const uint32_t n = sh.Lsq - 1u - sh.cr_s, base = (n & ~31u) + 4u * li;
+                        gmask = 0;
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)
+                            if (base + ((k + sub) & 3u) < n) gmask |= 1u << (8u * k);
+                    }
                     if (predict && flex) {
                         const uint32_t rest = 2u * sh.Lsq + sh.Lp;
                         // relative to the first byte of the sequence line (lane 0 looks at the record start)
