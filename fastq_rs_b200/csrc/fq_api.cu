@@ -36,6 +36,19 @@ __global__ void fq_init_kernel(DevResult* r, int spec_fail, int line_phase)
     r->n_win_scan = 0;
 }
 
+// streaming with FQB_F_INDEX into PINNED caller memory: the line ends of one chunk go straight to the mapped
+// host buffer, at the running line count the carry holds -- no host round trip per chunk
+__global__ void __launch_bounds__(256) fq_index_out_kernel(const uint32_t* __restrict__ idx, const DevResult* r,
+                                                           const DevCarry* carry, uint32_t* out, unsigned long long cap)
+{
+    const unsigned long long n = r->n_lines;
+    const unsigned long long off = carry->n_lines - n;          // fq_finalize_kernel has added this chunk already
+    const unsigned long long m = off >= cap ? 0ull : (n < cap - off ? n : cap - off);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+        out[off + i] = idx[i];
+}
+
 struct Slot {  // one stage of the streaming ring
     uint8_t* h_pinned = nullptr;
     cudaEvent_t copied = nullptr;  // H2D of the chunk in this host slot finished
@@ -107,6 +120,7 @@ struct fqb_ctx {
     bool last_byte_nl = true;        // last byte copied so far is '\n' (true before the first byte)
     // host index collection (generic closure path)
     uint32_t* host_index = nullptr;
+    uint32_t* host_index_dev = nullptr;   // device alias of host_index when the caller's buffer is pinned
     uint64_t host_index_cap = 0, host_index_n = 0;
 };
 
@@ -631,8 +645,14 @@ static int launch_pending(fqb_ctx* ctx, uint64_t next_bytes, bool eof)
     }
     int rc = enqueue_parse(ctx, &sh, ctx->s_comp, ctx->d_carry, ctx->d_total, false);
     if (rc) return rc;
-    if (ctx->stream_flags & FQB_F_INDEX) {
-        // generic-closure path: bring this chunk's line ends to the host (needs the count first)
+    if ((ctx->stream_flags & FQB_F_INDEX) && ctx->host_index_dev) {
+        // generic-closure path, pinned index buffer: written by the device, in stream order
+        fq_index_out_kernel<<<ctx->num_sms * 2, 256, 0, ctx->s_comp>>>(sh.d_index, ctx->d_res, ctx->d_carry,
+                                                                       ctx->host_index_dev, ctx->host_index_cap);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    } else if (ctx->stream_flags & FQB_F_INDEX) {
+        // pageable index buffer: bring this chunk's line ends to the host (needs the count first)
         CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, ctx->s_comp));
         CK(cudaStreamSynchronize(ctx->s_comp));
         uint64_t nl = ctx->h_res->n_lines;
@@ -733,6 +753,7 @@ static int stream_drain(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
     res->tail_offset = ctx->h_carry->tail_plus1 ? ctx->h_carry->tail_plus1 - 1 : UINT64_MAX;
     res->line_phase = 0;
     res->reserved = 0;
+    if (ctx->host_index_dev) ctx->host_index_n = std::min<uint64_t>(ctx->h_carry->n_lines, ctx->host_index_cap);
     ctx->streaming = false;
     return FQB_OK;
 }
@@ -766,6 +787,16 @@ int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint32_t flag
     ctx->host_index = host_index;
     ctx->host_index_cap = host_index ? index_cap : 0;
     ctx->stream_partial = (flags & FQB_F_PARTIAL) != 0;
+    ctx->host_index_dev = nullptr;
+    if (ctx->host_index_cap) {
+        cudaPointerAttributes ia;
+        void* dev = nullptr;
+        if (cudaPointerGetAttributes(&ia, host_index) == cudaSuccess && ia.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&dev, host_index, 0) == cudaSuccess)
+            ctx->host_index_dev = static_cast<uint32_t*>(dev);
+        else
+            cudaGetLastError();
+    }
     // pinned caller memory is copied from directly; pageable memory goes through the pinned slots
     cudaPointerAttributes attr;
     bool pinned = false;
@@ -805,6 +836,7 @@ int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint32_t flag
     ctx->streaming = false;
     if (n_index) *n_index = ctx->host_index_n;
     ctx->host_index = nullptr;
+    ctx->host_index_dev = nullptr;
     ctx->host_index_cap = 0;
     return rc;
 }

@@ -184,7 +184,9 @@ int fqb_fetch_filter(fqb_ctx *ctx, void *stream, uint64_t *n_kept, uint64_t *out
 /* ---- host path: bytes in host memory, staged through the pinned ring --------------------
  * replaces Parser::new(reader).each(stats closure) end to end.  Synchronous.
  * host_index (optional): receives the low 32 bits of the stream offset of every '\n'
- * before the first bad record, up to index_cap entries; *n_index = entries written.
+ * before the first bad record, up to index_cap entries; *n_index = entries written.  A host_index in
+ * pinned memory (fqb_host_alloc) is written by the device in stream order, with no synchronisation
+ * per chunk; pageable memory costs one per chunk.
  * flags: FQB_F_HIST | FQB_F_INDEX | FQB_F_PARTIAL.  With FQB_F_PARTIAL the call is one refill of a
  * longer stream (bounded-memory each()/record_sets(): src/lib.rs:262-294, 364-425): offsets are
  * relative to `bytes`, which must start at a record start. */

@@ -709,6 +709,38 @@ def test_streaming_small_slots(fq, oracle):
         e.close()
 
 
+def test_parse_host_pinned_index(fq, oracle):
+    """A host_index in pinned memory is written by the device chunk by chunk (no synchronisation per
+    chunk); same entries as the pageable path, also with an error in a late chunk and a small cap."""
+    import ctypes
+    from fastq_rs_b200 import _lib
+    L = _lib.lib()
+    e = fq.Engine(max_len=150, slot_bytes=2 * 68 * 1024, n_slots=2)
+    try:
+        good = oracle.synth_fixed_records(9000).tobytes()
+        bad = bytearray(good)
+        bad[7000 * 321] = ord("X")
+        for data, cap in ((good, 36000), (bytes(bad), 36000), (good, 1001), (good[:-1], 36000), (b"", 16)):
+            ores, oidx = oracle.each_index(data)
+            _, _, want = e.parse_host(data, hist=False, want_index=True, want_stats=False)    # pageable buffer
+            p = ctypes.c_void_p()
+            assert L.fqb_host_alloc(cap * 4, ctypes.byref(p)) == 0
+            res, got = _lib.Result(), ctypes.c_uint64(0)
+            a = np.frombuffer(data, dtype=np.uint8)
+            rc = L.fqb_parse_host(e.ctx, a.ctypes.data if a.size else None, a.size, _lib.F_INDEX, ctypes.byref(res), None,
+                                  p, cap, ctypes.byref(got))
+            assert rc == 0 and (res.status, res.n_records) == (ores.status, ores.n_records)
+            idx = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), shape=(cap,))
+            n = min(cap, want.size)
+            assert got.value == n
+            np.testing.assert_array_equal(idx[:n].astype(np.uint64), want[:n])
+            np.testing.assert_array_equal(idx[:min(n, 4 * ores.n_records)].astype(np.uint64),
+                                          oidx[:, 1:5].reshape(-1)[:min(n, 4 * ores.n_records)])
+            L.fqb_host_free(p)
+    finally:
+        e.close()
+
+
 class _ShortReader:
     """A reader that returns short, ragged reads (no readinto)."""
 
