@@ -887,6 +887,33 @@ def test_filter_nonzero_stream_offset_and_wrap(fq, torch, oracle, eng):
         assert dst[:len(want)].cpu().numpy().tobytes() == want
 
 
+def test_filter_shard_that_starts_inside_a_record(fq, torch, oracle, eng):
+    """A later shard of a stream: its index begins with the line ends of the record cut by the shard start;
+    the filter is handed the index from the first whole record on (not 16-byte aligned) and that record's offset."""
+    recs = [_rec(i, int(L)) for i, L in enumerate(np.random.default_rng(5).integers(20, 120, 3000))]
+    for k in (2, 7):                                   # plant lowercase bases in a few records
+        for j in range(k, 3000, 9):
+            r = bytearray(recs[j]); r[r.index(b"\n") + 3] = ord("a"); recs[j] = bytes(r)
+    data = b"".join(recs)
+    starts = np.cumsum([0] + [len(r) for r in recs])
+    for cut_rec, inside in ((100, 7), (555, 1), (1200, 30), (2000, 16)):
+        c = (int(starts[cut_rec]) + inside) // 16 * 16      # shard start, inside record `cut_rec` (or at its start)
+        rec0 = int(np.searchsorted(starts, c, side="left"))  # first record that starts in the shard
+        shard = data[c:]
+        d = to_dev(torch, shard)
+        idx = torch.zeros(len(shard) + 8, dtype=torch.int32, device="cuda")
+        eng.parse_device(d, n_own=len(shard), n_avail=len(shard), hist=False, index=idx, stream_offset=c,
+                         line_base=data[:c].count(b"\n"), line_start=(c == 0 or data[c - 1:c] == b"\n"))
+        out, _ = eng.fetch(want_stats=False)
+        assert out.status == 0 and out.n_records == 3000 - rec0
+        K = data[c:int(starts[rec0])].count(b"\n")          # line ends of the cut record that lie in the shard
+        _, n_kept, want = oracle.each_filter(data[int(starts[rec0]):], 1)
+        dst = torch.zeros(len(shard), dtype=torch.uint8, device="cuda")
+        eng.filter_device(d, idx[K:], out.n_records, fq._lib.KEEP_DNA, dst, stream_offset=c, first_offset=int(starts[rec0]))
+        assert eng.fetch_filter() == (n_kept, len(want))
+        assert dst[:len(want)].cpu().numpy().tobytes() == want
+
+
 def test_parser_filter_to(fq, oracle, eng):
     data = _filter_cases(oracle)["mixed"]
     for keep, mode in (("all", 0), ("dna", 1), ("dnan", 2)):
