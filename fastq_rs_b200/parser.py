@@ -337,7 +337,7 @@ class Parser:
         kernels drain the slots behind it.  In-memory inputs skip the thread and go through
         fqb_parse_host."""
         r = self._reader
-        if isinstance(r, (bytes, bytearray, memoryview, np.ndarray)) or not hasattr(r, "readinto"):
+        if isinstance(r, (bytes, bytearray, memoryview, np.ndarray)):
             data = _read_all(r)
             outcome, st, _ = self._engine.parse_host(data, hist=hist, want_stats=hist)
             return outcome, st
@@ -349,7 +349,13 @@ class Parser:
             try:
                 while True:
                     slot = eng.stream_acquire()                  # blocks until a pinned slot is free
-                    n = r.readinto(memoryview(slot).cast("B"))   # one read per slot, may be short
+                    mv = memoryview(slot).cast("B")
+                    if hasattr(r, "readinto"):
+                        n = r.readinto(mv)                       # one read per slot, may be short
+                    else:
+                        b = r.read(len(mv))
+                        n = len(b)
+                        mv[:n] = b
                     eng.stream_submit(n or 0)
                     if not n:
                         return
@@ -382,7 +388,9 @@ class Parser:
         """Write the records whose seq() passes validate_dna ("dna") / validate_dnan ("dnan") -- or
         every record ("all") -- to `writer`, verbatim (Record::write, src/records.rs:93-96) and in
         order; predicate and compaction run on the GPU.  Returns the number of records written;
-        raises FastqError after the records in front of a bad one have been written (each()'s order)."""
+        raises FastqError after the records in front of a bad one have been written (each()'s order).
+        (The whole input is staged in HBM at once: inputs larger than the GPU are fed shard by shard
+        through Engine.parse_device / Engine.filter_device.)"""
         import torch
         from ._lib import KEEP_ALL, KEEP_DNA, KEEP_DNAN
         mode = {"all": KEEP_ALL, "dna": KEEP_DNA, "dnan": KEEP_DNAN}[keep]

@@ -774,6 +774,12 @@ def test_each_over_a_reader_in_refills(chunk, fq, oracle, eng):
     for k, data in enumerate(cases):
         ores, oidx = oracle.each_index(data)
         for with_readinto in (False, True):
+            # the fast paths over the same reader (pinned ring fed by read() or readinto())
+            try:
+                assert fq.Parser(_ShortReader(data, with_readinto), engine=eng).count() == ores.n_records
+                assert ores.status == 0
+            except fq.FastqError as e:
+                assert e.status == ores.status and e.n_delivered == ores.n_records
             seen, err = [], None
             try:
                 fin = fq.Parser(_ShortReader(data, with_readinto), engine=eng, chunk_bytes=chunk).each(
