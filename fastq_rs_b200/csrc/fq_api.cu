@@ -82,10 +82,9 @@ struct fqb_ctx {
     size_t index_stage_cap = 0;
     unsigned long long* d_linecount = nullptr;
     // record filter workspace (grown on demand)
-    uint32_t* d_fkeep = nullptr;
-    unsigned long long* d_fblk = nullptr;
-    size_t fkeep_cap = 0, fblk_cap = 0;
-    unsigned long long* d_fmisc = nullptr;   // wraps [1 + FILTER_MAX_WRAPS] then result [4]
+    unsigned long long* d_fblk = nullptr;    // look-back descriptors, one per 256 records
+    size_t fblk_cap = 0;
+    unsigned long long* d_fmisc = nullptr;   // wraps [1 + FILTER_MAX_WRAPS], result [4], ticket [1]
     unsigned long long* h_fres = nullptr;    // pinned [4]
     DevResult* h_res = nullptr;  // pinned
     unsigned long long* h_linecount = nullptr;
@@ -258,7 +257,6 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaFree(ctx->d_index_stage);
     cudaFree(ctx->d_linecount);
     cudaFree(ctx->d_carry);
-    cudaFree(ctx->d_fkeep);
     cudaFree(ctx->d_fblk);
     cudaFree(ctx->d_fmisc);
     if (ctx->h_fres) cudaFreeHost(ctx->h_fres);
@@ -481,23 +479,15 @@ int fqb_filter_device(fqb_ctx* ctx, const uint8_t* d_bytes, uint64_t stream_offs
     CK(cudaSetDevice(ctx->device));
     const size_t nblk = (size_t)((n_records + 255) / 256);
     if (!ctx->d_fmisc) {
-        CK(cudaMalloc(&ctx->d_fmisc, (1 + FILTER_MAX_WRAPS + 4) * 8));
+        CK(cudaMalloc(&ctx->d_fmisc, (1 + FILTER_MAX_WRAPS + 4 + 1) * 8));
         CK(cudaHostAlloc(&ctx->h_fres, 4 * 8, cudaHostAllocDefault));
     }
-    if (n_records > ctx->fkeep_cap) {   // the previous call may still be running on another stream: wait for it
-        CK(cudaDeviceSynchronize());
-        cudaFree(ctx->d_fkeep);
-        ctx->d_fkeep = nullptr;
-        ctx->fkeep_cap = 0;
-        CK(cudaMalloc(&ctx->d_fkeep, (size_t)n_records * 4));
-        ctx->fkeep_cap = n_records;
-    }
-    if (nblk > ctx->fblk_cap) {
+    if (nblk > ctx->fblk_cap) {   // the previous call may still be running on another stream: wait for it
         CK(cudaDeviceSynchronize());
         cudaFree(ctx->d_fblk);
         ctx->d_fblk = nullptr;
         ctx->fblk_cap = 0;
-        CK(cudaMalloc(&ctx->d_fblk, nblk * 16));
+        CK(cudaMalloc(&ctx->d_fblk, nblk * 8));
         ctx->fblk_cap = nblk;
     }
     FilterParams p;
@@ -507,8 +497,8 @@ int fqb_filter_device(fqb_ctx* ctx, const uint8_t* d_bytes, uint64_t stream_offs
     p.stream_offset = stream_offset;
     p.first_offset = first_offset;
     p.mode = mode;
-    p.keep = ctx->d_fkeep;
     p.blk = ctx->d_fblk;
+    p.ticket = reinterpret_cast<unsigned int*>(ctx->d_fmisc + 1 + FILTER_MAX_WRAPS + 4);
     p.wraps = ctx->d_fmisc;
     p.out = d_out;
     p.out_cap = out_cap;

@@ -109,9 +109,9 @@ struct FilterParams {
     unsigned long long stream_offset;  // stream offset of data[0]
     unsigned long long first_offset;   // stream offset of the first byte of record 0
     uint32_t mode;                     // 0 keep all, 1 validate_dna, 2 validate_dnan
-    uint32_t* keep;                    // [n_records] record bytes if kept, else 0
-    unsigned long long* blk;           // [2 * blocks] kept bytes (-> exclusive prefix), kept records
-    unsigned long long* wraps;         // [0] count, [1..] records at which the 32-bit offsets wrap
+    unsigned long long* blk;           // [blocks] look-back descriptors: status | kept bytes (total, then prefix)
+    unsigned int* ticket;              // order in which the blocks enter the look-back chain
+    unsigned long long* wraps;         // [0] count, [1..] records at which the 32-bit offsets wrap; result follows
     uint8_t* out;
     unsigned long long out_cap;
     unsigned long long* result;        // [0] records kept [1] bytes kept [2] wraps seen

@@ -8,13 +8,19 @@
 //   src/records.rs:93-96   RefRecord::write = the record's raw bytes, '@' .. final '\n', unchanged
 //
 // Input: the shard's bytes and the line-end index a finished fqb_parse_device wrote (4 x u32 per record =
-// low 32 bits of the stream offsets of its four '\n').  HBM-bound byte work, four small kernels:
+// low 32 bits of the stream offsets of its four '\n').  HBM-bound byte work: the input is read once, the
+// survivors are written once.
 //   fq_filter_wraps_kernel  the (very few) records at which the 32-bit offsets wrap (one per 4 GiB)
-//   fq_filter_mark_kernel   one thread per record: predicate over the sequence line (aligned 4-byte words,
-//                           SWAR membership test), keep[k] = record bytes or 0, per-block sums
-//   fq_filter_scan_kernel   exclusive prefix of the per-block kept bytes (one CTA)
-//   fq_filter_copy_kernel   block-local prefix, then one warp per kept record copies it with dst-aligned
-//                           4-byte stores (source words funnel-shifted into place)
+//   fq_filter_kernel        one CTA per 256 records, taken in ticket order:
+//                           (1) one thread per record: predicate over the sequence line (aligned 16-byte loads,
+//                               SWAR membership test) -> bytes this record contributes (0 if dropped);
+//                           (2) block prefix of those bytes; the block total is published and the block's
+//                               offset in the output comes from a decoupled look-back over the totals /
+//                               prefixes of the blocks before it (single pass, no second read of the input);
+//                           (3) consecutive survivors are adjacent in the input and in the output: each warp
+//                               copies whole runs with dst-aligned 16-byte stores (source words funnel-shifted
+//                               into place, all loads of a run issued before its first store) -- the bytes
+//                               were just touched by (1), so most of them come from L1/L2.
 #include "fq_common.cuh"
 #include "fq_device.cuh"
 
@@ -82,92 +88,6 @@ __device__ __forceinline__ bool seq_ok(const uint8_t* __restrict__ d, unsigned l
     return bad == 0;
 }
 
-__global__ void __launch_bounds__(FBLOCK) fq_filter_mark_kernel(const FilterParams p)
-{
-    __shared__ unsigned long long s_bytes[FBLOCK / 32], s_cnt[FBLOCK / 32];
-    const unsigned long long k = (unsigned long long)blockIdx.x * FBLOCK + threadIdx.x;
-    const uint32_t nwr = (uint32_t)min(p.wraps[0], (unsigned long long)FILTER_MAX_WRAPS);
-    uint32_t len = 0;
-    if (k < p.n_records) {
-        uint4 e;
-        if ((reinterpret_cast<uintptr_t>(p.index) & 15) == 0) {
-            e = __ldg(reinterpret_cast<const uint4*>(p.index) + k);
-        } else {   // an index that starts at the shard's phase (not a multiple of 4 entries in)
-            e.x = __ldg(p.index + 4 * k);
-            e.y = __ldg(p.index + 4 * k + 1);
-            e.z = __ldg(p.index + 4 * k + 2);
-            e.w = __ldg(p.index + 4 * k + 3);
-        }
-        const uint32_t prev_lo = k ? __ldg(p.index + 4 * k - 1) : (uint32_t)(p.first_offset - 1);
-        const unsigned long long pos = record_pos(p, k, prev_lo, p.wraps, nwr);
-        const uint32_t s_lo = prev_lo + 1;
-        const uint32_t h = e.x - s_lo, sq = e.y - s_lo, q = e.w - s_lo;   // record-relative line ends
-        unsigned long long a0 = pos + h + 1, a1 = pos + sq;
-        if (a1 > a0 && p.data[a1 - 1] == '\r') --a1;                      // trim_winline, src/records.rs:65-73
-        bool ok = true;
-        if (p.mode == 1)
-            ok = seq_ok(p.data, a0, a1, (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20));                // A C G T
-        else if (p.mode == 2)
-            ok = seq_ok(p.data, a0, a1, (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20) | (1u << 14));   // + N
-        len = ok ? q + 1 : 0;
-        p.keep[k] = len;
-    }
-    unsigned long long b = warp_sum_u64(len), c = warp_sum_u64(len ? 1ull : 0ull);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        s_bytes[warp] = b;
-        s_cnt[warp] = c;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        b = c = 0;
-        for (int i = 0; i < FBLOCK / 32; ++i) {
-            b += s_bytes[i];
-            c += s_cnt[i];
-        }
-        p.blk[2 * (size_t)blockIdx.x] = b;
-        p.blk[2 * (size_t)blockIdx.x + 1] = c;
-    }
-}
-
-// one CTA: blk[2b] <- exclusive prefix of the kept bytes; result = totals
-__global__ void __launch_bounds__(1024) fq_filter_scan_kernel(const FilterParams p, unsigned long long nblk)
-{
-    __shared__ unsigned long long s[1024];
-    __shared__ unsigned long long s_cnt[32];
-    const int t = threadIdx.x;
-    const unsigned long long per = (nblk + 1023) / 1024;
-    const unsigned long long b0 = min(nblk, per * t), b1 = min(nblk, b0 + per);
-    unsigned long long bytes = 0, cnt = 0;
-    for (unsigned long long b = b0; b < b1; ++b) {
-        bytes += p.blk[2 * b];
-        cnt += p.blk[2 * b + 1];
-    }
-    s[t] = bytes;
-    cnt = warp_sum_u64(cnt);
-    if ((t & 31) == 0) s_cnt[t >> 5] = cnt;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const unsigned long long v = t >= d ? s[t - d] : 0;
-        __syncthreads();
-        s[t] += v;
-        __syncthreads();
-    }
-    unsigned long long run = s[t] - bytes;   // exclusive
-    for (unsigned long long b = b0; b < b1; ++b) {
-        const unsigned long long v = p.blk[2 * b];
-        p.blk[2 * b] = run;
-        run += v;
-    }
-    if (t == 0) {
-        unsigned long long c = 0;
-        for (int i = 0; i < 32; ++i) c += s_cnt[i];
-        p.result[0] = c;
-        p.result[1] = s[1023];
-        p.result[2] = p.wraps[0];
-    }
-}
-
 // copy n bytes with all 32 lanes: dst-aligned 16-byte stores, two chunks per lane in flight; source words are
 // funnel-shifted into place unless source and destination are congruent mod 16 (then plain 16-byte loads)
 __device__ __forceinline__ uint4 load_shifted(const uint32_t* __restrict__ sa, uint32_t sh)
@@ -220,32 +140,102 @@ __device__ __forceinline__ void copy_run(const uint8_t* __restrict__ src, uint8_
     }
 }
 
-__global__ void __launch_bounds__(FBLOCK) fq_filter_copy_kernel(const FilterParams p)
+// descriptor of a block in the look-back chain: status in the two top bits, bytes below
+static constexpr unsigned long long F_AGG = 1ull << 62, F_PRE = 2ull << 62, F_VAL = (1ull << 62) - 1ull;
+
+__global__ void __launch_bounds__(FBLOCK) fq_filter_kernel(const FilterParams p)
 {
     __shared__ uint32_t s_warp[FBLOCK / 32];
-    const unsigned long long k = (unsigned long long)blockIdx.x * FBLOCK + threadIdx.x;
+    __shared__ uint32_t s_cnt[FBLOCK / 32];
+    __shared__ unsigned long long s_excl;
+    __shared__ unsigned int s_block;
+    if (threadIdx.x == 0) s_block = atomicAdd(p.ticket, 1u);   // blocks enter the chain in the order they start
+    __syncthreads();
+    const unsigned long long blk = s_block;
+    const unsigned long long k = blk * FBLOCK + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nwr = (uint32_t)min(p.wraps[0], (unsigned long long)FILTER_MAX_WRAPS);
+
+    // (1) predicate
     uint32_t len = 0;
     unsigned long long pos = 0;
     if (k < p.n_records) {
-        len = p.keep[k];
+        uint4 e;
+        if ((reinterpret_cast<uintptr_t>(p.index) & 15) == 0) {
+            e = __ldg(reinterpret_cast<const uint4*>(p.index) + k);
+        } else {   // an index that starts at the shard's phase (not a multiple of 4 entries in)
+            e.x = __ldg(p.index + 4 * k);
+            e.y = __ldg(p.index + 4 * k + 1);
+            e.z = __ldg(p.index + 4 * k + 2);
+            e.w = __ldg(p.index + 4 * k + 3);
+        }
         const uint32_t prev_lo = k ? __ldg(p.index + 4 * k - 1) : (uint32_t)(p.first_offset - 1);
         pos = record_pos(p, k, prev_lo, p.wraps, nwr);
+        const uint32_t s_lo = prev_lo + 1;
+        const uint32_t h = e.x - s_lo, sq = e.y - s_lo, q = e.w - s_lo;   // record-relative line ends
+        unsigned long long a0 = pos + h + 1, a1 = pos + sq;
+        if (a1 > a0 && p.data[a1 - 1] == '\r') --a1;                      // trim_winline, src/records.rs:65-73
+        bool ok = true;
+        if (p.mode == 1)
+            ok = seq_ok(p.data, a0, a1, (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20));                // A C G T
+        else if (p.mode == 2)
+            ok = seq_ok(p.data, a0, a1, (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20) | (1u << 14));   // + N
+        len = ok ? q + 1 : 0;
     }
-    uint32_t incl = len;   // inclusive warp prefix of the kept bytes
+
+    // (2) block prefix, then the block's place in the output
+    uint32_t incl = len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += v;
     }
+    const uint32_t cnt = (uint32_t)__popc(__ballot_sync(0xffffffffu, len != 0));
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
     uint32_t before = 0;
     for (int i = 0; i < warp; ++i) before += s_warp[i];
-    const unsigned long long dst = p.blk[2 * (size_t)blockIdx.x] + before + (incl - len);
+    if (warp == 0) {
+        unsigned long long total = 0, kept = 0;
+        for (int i = 0; i < FBLOCK / 32; ++i) {
+            total += s_warp[i];
+            kept += s_cnt[i];
+        }
+        volatile unsigned long long* desc = p.blk;
+        if (lane == 0) {
+            desc[blk] = (blk == 0 ? F_PRE : F_AGG) | total;
+            if (kept) atomicAdd(p.result + 0, kept);
+            if (total) atomicAdd(p.result + 1, total);
+        }
+        // decoupled look-back: lane l looks at block blk - 1 - l of the current group of 32
+        unsigned long long excl = 0;
+        long long j = (long long)blk - 1;
+        while (j >= 0) {
+            const long long mine = j - lane;
+            unsigned long long d = F_PRE;                       // blocks in front of block 0: prefix 0
+            if (mine >= 0) {
+                do {
+                    d = desc[mine];
+                } while ((d & ~F_VAL) == 0);
+            }
+            const unsigned pre = __ballot_sync(0xffffffffu, (d & F_PRE) != 0);
+            const int stop = __ffs(pre) - 1;                    // nearest block that already knows its prefix
+            unsigned long long v = (stop < 0 || lane <= stop) ? (d & F_VAL) : 0ull;
+            excl += warp_sum_u64(v);
+            if (stop >= 0) break;
+            j -= 32;
+        }
+        if (lane == 0) {
+            if (blk != 0) desc[blk] = F_PRE | (excl + total);
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+
+    // (3) copy the survivors
+    const unsigned long long dst = s_excl + before + (incl - len);
     if (dst + len > p.out_cap) len = 0;   // what does not fit is not written (out_bytes tells)
-    // consecutive kept records are adjacent in the input and in the output: copy them as one run
     const uint32_t kept = __ballot_sync(0xffffffffu, len != 0);
     uint32_t starts = kept & ~(kept << 1);
     while (starts) {
@@ -259,22 +249,30 @@ __global__ void __launch_bounds__(FBLOCK) fq_filter_copy_kernel(const FilterPara
     }
 }
 
+__global__ void fq_filter_finish_kernel(const FilterParams p)
+{
+    p.result[2] = p.wraps[0];
+}
+
 cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(p.wraps, 0, (1 + FILTER_MAX_WRAPS) * sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
     const unsigned long long nblk = (p.n_records + FBLOCK - 1) / FBLOCK;
-    if (p.n_records) {
+    cudaError_t e = cudaMemsetAsync(p.wraps, 0, (1 + FILTER_MAX_WRAPS + 4) * sizeof(unsigned long long), st);   // + result
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    if (nblk) {
+        e = cudaMemsetAsync(p.blk, 0, nblk * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
         const unsigned long long want = (p.n_records + 255) / 256;
         const int grid = (int)(want < (unsigned long long)num_sms * 8 ? want : (unsigned long long)num_sms * 8);
         fq_filter_wraps_kernel<<<grid, 256, 0, st>>>(p);
-        fq_filter_mark_kernel<<<(unsigned)nblk, FBLOCK, 0, st>>>(p);
+        fq_filter_kernel<<<(unsigned)nblk, FBLOCK, 0, st>>>(p);
     }
-    fq_filter_scan_kernel<<<1, 1024, 0, st>>>(p, nblk);
-    if (p.n_records) fq_filter_copy_kernel<<<(unsigned)nblk, FBLOCK, 0, st>>>(p);
+    fq_filter_finish_kernel<<<1, 1, 0, st>>>(p);
     return cudaGetLastError();
 }
 
-int filter_launches(unsigned long long n_records) { return n_records ? 4 : 1; }
+int filter_launches(unsigned long long n_records) { return n_records ? 3 : 1; }
 
 }  // namespace fq
