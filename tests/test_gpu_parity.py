@@ -957,6 +957,20 @@ def test_fastq_count_example_on_a_10mb_file(fq, oracle, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     got = subprocess.check_output([sys.executable, os.path.join(root, "examples", "fastq_count.py"), str(path)], text=True)
     assert int(got.strip()) == n_rec
+    # the other example programs of the reference (fastq-count-thread.rs, multiple-files.rs) and the stats / filter CLI
+    ex = os.path.join(root, "examples")
+    got = subprocess.check_output([sys.executable, os.path.join(ex, "fastq_count_thread.py"), str(path), "3"], text=True)
+    assert int(got.strip()) == n_rec
+    path2 = tmp_path / "reads2.fastq"
+    path2.write_bytes(data[:321 * 1000])
+    got = subprocess.check_output([sys.executable, os.path.join(ex, "multiple_files.py"), str(path), str(path2)], text=True)
+    assert got.strip() == f"Number of reads: ({n_rec}, 1000)"
+    got = subprocess.check_output([sys.executable, os.path.join(ex, "fastq_stats_filter.py"), "stats", str(path)], text=True)
+    assert got.splitlines()[0].startswith(f"records {n_rec}  bases {n_rec * 150}") and len(got.splitlines()) == 151
+    kept = tmp_path / "kept.fastq"
+    got = subprocess.check_output([sys.executable, os.path.join(ex, "fastq_stats_filter.py"), "filter", str(path), str(kept), "dna"], text=True)
+    _, n_kept, want = oracle.each_filter(data, 1)
+    assert int(got.strip()) == n_kept and kept.read_bytes() == want
     # a truncated file raises the reference's error after counting nothing more
     bad = tmp_path / "bad.fastq"
     bad.write_bytes(data[:-1])
