@@ -92,9 +92,9 @@ __device__ __forceinline__ bool seq_ok(const uint8_t* __restrict__ d, unsigned l
 // funnel-shifted into place unless source and destination are congruent mod 16 (then plain 16-byte loads)
 __device__ __forceinline__ uint4 load_shifted(const uint32_t* __restrict__ sa, uint32_t sh)
 {
-    const uint32_t w0 = __ldg(sa), w1 = __ldg(sa + 1), w2 = __ldg(sa + 2), w3 = __ldg(sa + 3);
+    const uint32_t w0 = __ldcs(sa), w1 = __ldcs(sa + 1), w2 = __ldcs(sa + 2), w3 = __ldcs(sa + 3);
     // the fifth word holds bytes of this run whenever sh != 0, so the aligned load stays inside its page
-    const uint32_t w4 = sh ? __ldg(sa + 4) : 0u;
+    const uint32_t w4 = sh ? __ldcs(sa + 4) : 0u;
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                       __funnelshift_r(w3, w4, sh));
 }
@@ -113,30 +113,30 @@ __device__ __forceinline__ void copy_run(const uint8_t* __restrict__ src, uint8_
     // first 32 chunks + head + tail: every load is issued before the first store (one memory latency per run)
     uint8_t hb = 0, tb = 0;
     uint4 x = make_uint4(0, 0, 0, 0);
-    if ((unsigned long long)lane < h) hb = __ldg(src + lane);
-    if ((unsigned long long)lane < t) tb = __ldg(src + o + lane);
-    if ((unsigned long long)lane < body) x = aligned ? __ldg(sv + lane) : load_shifted(sa + 4 * lane, sh);
+    if ((unsigned long long)lane < h) hb = __ldcs(src + lane);
+    if ((unsigned long long)lane < t) tb = __ldcs(src + o + lane);
+    if ((unsigned long long)lane < body) x = aligned ? __ldcs(sv + lane) : load_shifted(sa + 4 * lane, sh);
     if ((unsigned long long)lane < h) dst[lane] = hb;
     if ((unsigned long long)lane < t) dst[o + lane] = tb;
-    if ((unsigned long long)lane < body) d[lane] = x;
+    if ((unsigned long long)lane < body) __stcs(d + lane, x);
     if (body <= 32) return;
     unsigned long long c = lane + 32;
     if (aligned) {
         for (; c + 96 < body; c += 128) {
-            const uint4 x0 = __ldg(sv + c), x1 = __ldg(sv + c + 32), x2 = __ldg(sv + c + 64), x3 = __ldg(sv + c + 96);
-            d[c] = x0;
-            d[c + 32] = x1;
-            d[c + 64] = x2;
-            d[c + 96] = x3;
+            const uint4 x0 = __ldcs(sv + c), x1 = __ldcs(sv + c + 32), x2 = __ldcs(sv + c + 64), x3 = __ldcs(sv + c + 96);
+            __stcs(d + c, x0);
+            __stcs(d + c + 32, x1);
+            __stcs(d + c + 64, x2);
+            __stcs(d + c + 96, x3);
         }
-        for (; c < body; c += 32) d[c] = __ldg(sv + c);
+        for (; c < body; c += 32) __stcs(d + c, __ldcs(sv + c));
     } else {
         for (; c + 32 < body; c += 64) {
             const uint4 x0 = load_shifted(sa + 4 * c, sh), x1 = load_shifted(sa + 4 * (c + 32), sh);
-            d[c] = x0;
-            d[c + 32] = x1;
+            __stcs(d + c, x0);
+            __stcs(d + c + 32, x1);
         }
-        for (; c < body; c += 32) d[c] = load_shifted(sa + 4 * c, sh);
+        for (; c < body; c += 32) __stcs(d + c, load_shifted(sa + 4 * c, sh));
     }
 }
 
