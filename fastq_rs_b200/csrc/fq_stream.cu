@@ -602,7 +602,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t K = (line_start && phase == 0) ? 0u : 4u - phase;
                 c = K + neg <= nstored ? K + neg : NO_START;
             }
-            if (c == NO_START || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+            // (bytes >= 0x80 only matter to the histogram addressing: without histograms any byte will do)
+            if (c == NO_START || (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
                 failed = true;
             } else {
                 cur = (unsigned long long)(w.src + (long long)list[c]);
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 uint32_t hib;
                 const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
                 const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
-                if (n_win == 0 || __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+                if (n_win == 0 || (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
                     failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
                     break;
                 }

@@ -488,6 +488,22 @@ def test_count_mode_prediction(where, torch, oracle, eng):
     assert (out.status != 0 and out.n_records == k) if where != "none" else out.n_records == 6000
 
 
+def test_count_mode_with_non_ascii_bytes(torch, oracle, eng):
+    """Without histograms nothing depends on the byte values beyond '\\n', '@', '+': ids, reads and qualities
+    with bytes >= 0x80 are delimited like any others (fixed and varying shapes)."""
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(5000):
+        L = 150 if i < 3000 else int(rng.integers(1, 200))
+        head = ("@r%d é\u00fc\u4e2d" % i).encode("utf-8")
+        seq = bytes(rng.integers(128, 256, L, dtype=np.uint8))
+        qual = bytes(rng.integers(128, 256, L, dtype=np.uint8))
+        recs.append(head + b"\n" + seq + b"\n+\n" + qual + b"\n")
+    data = b"".join(recs)
+    check_count_mode(torch, oracle, eng, data)
+    check_device_vs_oracle(torch, oracle, eng, data)          # with histograms: the exact path counts rows >= 128
+
+
 def test_count_mode_varying_shapes(torch, oracle, eng):
     data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
     check_count_mode(torch, oracle, eng, data)
