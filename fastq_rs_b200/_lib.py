@@ -30,7 +30,7 @@ SYMBOLS = [
     "fqb_device_stats", "fqb_device_result", "fqb_launch_count", "fqb_last_scan_ms", "fqb_parse_host",
     "fqb_stream_begin", "fqb_stream_acquire", "fqb_stream_submit", "fqb_stream_finish",
     "fqb_host_alloc", "fqb_host_free", "fqb_synth_fixed_device", "fqb_synth_var_device",
-    "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter",
+    "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter", "fqb_last_path",
 ]
 
 
@@ -128,6 +128,8 @@ def lib():
     L.fqb_synth_var_device.restype = i32
     L.fqb_synth_var_sizes_device.argtypes = [vp, u64, u64, u64, vp]
     L.fqb_synth_var_sizes_device.restype = i32
+    L.fqb_last_path.argtypes = [vp, C.POINTER(u64 * 3)]
+    L.fqb_last_path.restype = i32
     L.fqb_filter_device.argtypes = [vp, vp, u64, vp, u64, u64, u32, vp, u64, vp]
     L.fqb_filter_device.restype = i32
     L.fqb_fetch_filter.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64)]

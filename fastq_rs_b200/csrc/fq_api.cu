@@ -520,6 +520,15 @@ int fqb_fetch_filter(fqb_ctx* ctx, void* stream, uint64_t* n_kept, uint64_t* out
     return FQB_OK;
 }
 
+int fqb_last_path(fqb_ctx* ctx, uint64_t out[3])
+{
+    if (!ctx || !out || !ctx->h_res) return FQB_E_ARG;
+    out[0] = ctx->h_res->spec_fail ? 1 : 0;
+    out[1] = ctx->h_res->n_win_pred;
+    out[2] = ctx->h_res->n_win_scan;
+    return FQB_OK;
+}
+
 int fqb_host_alloc(uint64_t bytes, void** out)
 {
     if (!out) return FQB_E_ARG;

@@ -197,6 +197,13 @@ class Engine:
                "fqb_fetch_filter")
         return nk.value, nb.value
 
+    def last_path(self) -> dict:
+        """Which path produced the result of the last fetch(): {"exact": the speculative pass was abandoned,
+        "predicted": windows predicted, "scanned": windows scanned} (diagnostics)."""
+        out = (C.c_uint64 * 3)()
+        _check(self.ctx, self.L.fqb_last_path(self.ctx, C.byref(out)), "fqb_last_path")
+        return {"exact": bool(out[0]), "predicted": int(out[1]), "scanned": int(out[2])}
+
     def last_scan_ms(self) -> float:
         return float(self.L.fqb_last_scan_ms(self.ctx))
 

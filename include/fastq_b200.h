@@ -157,6 +157,10 @@ uint64_t *fqb_device_stats(fqb_ctx *ctx);
  * [4] err_offset [5] tail_offset (UINT64_MAX if none) [6] line_phase [7] reserved -- lets an N-rank
  * driver all-gather the outcomes without a host round trip */
 uint64_t *fqb_device_result(fqb_ctx *ctx);
+/* which path produced the result the last fqb_fetch returned (diagnostics; tests use it to make sure clean
+ * inputs stay on the fast path): out[0] = 1 if the speculative pass was abandoned and the exact kernel redid the
+ * shard, out[1] = windows the speculative kernel predicted, out[2] = windows it scanned */
+int fqb_last_path(fqb_ctx *ctx, uint64_t out[3]);
 /* number of kernels this library launched on ctx so far (bench accounting) */
 uint64_t fqb_launch_count(fqb_ctx *ctx);
 /* CUDA-event time of the main scan kernel of the last fqb_parse_device call, in ms

@@ -504,6 +504,39 @@ def test_count_mode_with_non_ascii_bytes(torch, oracle, eng):
     check_device_vs_oracle(torch, oracle, eng, data)          # with histograms: the exact path counts rows >= 128
 
 
+def test_clean_inputs_stay_on_the_fast_path(torch, oracle, eng, eng300):
+    """Guard against silent fallbacks (parity would still hold, throughput would not): clean inputs of every
+    BASELINE shape are served by the speculative kernel, fixed shapes almost entirely by predicted windows."""
+    def path(engine, t, n, hist, n_rec):
+        idx = torch.zeros(4 * n_rec + 8, dtype=torch.int32, device="cuda")
+        engine.parse_device(t, n_own=n, n_avail=n, hist=hist, index=idx)
+        out, _ = engine.fetch(want_stats=False)
+        assert out.status == 0 and out.n_records == n_rec
+        return engine.last_path()
+
+    def tiled(block: bytes, reps: int):
+        a = torch.from_numpy(np.frombuffer(block, dtype=np.uint8).copy()).cuda().repeat(reps)
+        return torch.cat([a, torch.zeros(64, dtype=torch.uint8, device="cuda")]), len(block) * reps
+
+    n_rec = 1600000                                     # 514 MB of fixed 150 bp records
+    t = torch.zeros(n_rec * 321 + 64, dtype=torch.uint8, device="cuda")
+    eng.synth_fixed(t, n_rec * 321)
+    for hist in (True, False):
+        p = path(eng, t, n_rec * 321, hist, n_rec)
+        assert not p["exact"] and p["predicted"] > 5 * p["scanned"], p
+    t, n = tiled(oracle.synth_var(20000).tobytes(), 20)            # variable 50-300 bp
+    for hist in (True, False):
+        p = path(eng300, t, n, hist, 20000 * 20)
+        assert not p["exact"] and p["scanned"] > 0, p
+    t, n = tiled(b"".join(_illumina(20000)), 30)                   # id lines of varying length
+    p = path(eng, t, n, True, 20000 * 30)
+    assert not p["exact"] and p["predicted"] > 5 * p["scanned"], p
+    assert not path(eng, t, n, False, 20000 * 30)["exact"]
+    utf8 = b"".join(("@r%d \u00e9\u4e2d" % i).encode() + b"\n" + _rec(i, 150)[_rec(i, 150).index(b"\n") + 1:] for i in range(5000))
+    t, n = tiled(utf8, 20)
+    assert not path(eng, t, n, False, 5000 * 20)["exact"]          # no histograms: byte values do not matter
+
+
 def test_count_mode_varying_shapes(torch, oracle, eng):
     data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
     check_count_mode(torch, oracle, eng, data)
