@@ -34,6 +34,7 @@ __global__ void fq_init_kernel(DevResult* r, int spec_fail, int line_phase)
     r->line_phase = line_phase;
     r->n_win_pred = 0;
     r->n_win_scan = 0;
+    r->tail_err = 0;
 }
 
 // streaming with FQB_F_INDEX into PINNED caller memory: the line ends of one chunk go straight to the mapped
@@ -381,6 +382,11 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         if (timed) ctx->ev_valid = fast || !(p.flags & F_INFER_START);
         if (fast && want_index) {
             CK(launch_stream_compact(p, carry, ctx->grid, st));
+            ctx->launches += 1;
+        }
+        if (fast && (p.flags & F_EOF) && !(p.flags & F_INFER_START)) {
+            // a bad record the speculative kernel found at the end of the stream: the line ends behind it
+            CK(launch_tail_index(p, carry, st));
             ctx->launches += 1;
         }
     }

@@ -38,6 +38,8 @@ struct DevResult {
     int line_phase;                 // line_base mod 4 implied by the first record start of the shard
     unsigned long long n_win_pred;  // windows of the speculative kernel that were predicted / scanned (FQB_DEBUG)
     unsigned long long n_win_scan;
+    int tail_err;                   // the speculative kernel itself found the first bad record: it lies in the last
+    int pad2;                       // range of an EOF shard, so nothing behind it was counted; first_bad holds it
 };
 
 // one contiguous range of tiles = the work of one CTA
@@ -134,6 +136,7 @@ cudaError_t stream_configure();
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
+cudaError_t launch_tail_index(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, unsigned long long* pub,
                             cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);

@@ -85,7 +85,9 @@ __global__ void fq_diagnose_kernel(const ScanParams p, DevCarry* carry)
 //   mode 1: before the launch restricted to the records in front of the first bad one
 __global__ void fq_rerun_reset_kernel(const ScanParams p, int mode)
 {
-    if (mode == 0 ? p.res->spec_fail == 0 : p.res->first_bad == NONE64) return;
+    // mode 0: the speculative pass was abandoned; mode 1: the exact pass found a bad record (a bad record the
+    // speculative pass found itself at the end of the shard needs no second pass: nothing behind it was counted)
+    if (mode == 0 ? p.res->spec_fail == 0 : (p.res->first_bad == NONE64 || p.res->tail_err)) return;
     const size_t n_stats = stats_words(p.max_len);
     const size_t n_seq = (size_t)p.max_len * 256;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -97,6 +99,7 @@ __global__ void fq_rerun_reset_kernel(const ScanParams p, int mode)
         if (i0 == 0) {
             p.res->first_bad = NONE64;
             p.res->tail_start = NONE64;
+            p.res->tail_err = 0;
         }
     }
 }
@@ -219,6 +222,63 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// tail_err: the speculative kernel found the first bad record itself, at the end of a stream; the line ends of
+// the bytes from that record on still belong to the shard's line count and index.  One CTA, 16 bytes per
+// thread and step (that tail is a truncated record or a few stray lines; the rare long one just takes longer).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) fq_tail_index_kernel(const ScanParams p, const DevCarry* carry)
+{
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned long long s_base;
+    DevResult* r = p.res;
+    if (!r->tail_err || r->spec_fail) return;
+    if (carry && carry->status != 0) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool want_index = (p.flags & F_INDEX) && p.index != nullptr && p.index_cap != 0;
+    if (t == 0) s_base = r->n_lines;
+    __syncthreads();
+    for (unsigned long long a = r->first_bad; a < p.n_own; a += 16384) {
+        const unsigned long long mine = a + 16ull * t;
+        unsigned m = 0;                                   // bit i = byte mine + i is a '\n' of the owned bytes
+        for (int i = 0; i < 16; ++i)
+            if (mine + i < p.n_own && p.data[mine + i] == '\n') m |= 1u << i;
+        const unsigned c = __popc(m);
+        unsigned incl = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (w < warp) before += s_warp[w];
+            total += s_warp[w];
+        }
+        unsigned long long rank = s_base + before + (incl - c);
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            if (want_index && rank < p.index_cap) p.index[rank] = (uint32_t)(p.stream_offset + mine + i);
+            ++rank;
+        }
+        __syncthreads();
+        if (t == 0) s_base += total;
+        __syncthreads();
+    }
+    if (t == 0) {
+        r->line_end += s_base - r->n_lines;
+        r->n_lines = s_base;
+    }
+}
+
+cudaError_t launch_tail_index(const ScanParams& p, DevCarry* carry, cudaStream_t st)
+{
+    fq_tail_index_kernel<<<1, 1024, 0, st>>>(p, carry);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

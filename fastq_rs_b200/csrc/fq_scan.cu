@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1) fq_scan_kernel(const __grid_constant_
     unsigned long long limit = NONE64;
     if (p.flags & F_RERUN) {
         limit = p.res->first_bad;                 // written by the earlier launches, stable during this one
-        if (limit == NONE64) return;
+        if (limit == NONE64 || p.res->tail_err) return;
     } else if (!p.res->spec_fail) {
         return;
     }

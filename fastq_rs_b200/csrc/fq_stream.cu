@@ -356,11 +356,16 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
                    c_qr = lds_u8(buf_s + e - 1u);
     // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
     const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
-    const bool ok = valid && good;
+    bool ok = valid && good;
     uint32_t first_bad = NO_START;
     {
         const unsigned nok = __ballot_sync(0xffffffffu, valid && !good);
-        if (nok) first_bad = 4u * pass + (((uint32_t)__ffs(nok) - 1u) >> 3);
+        if (nok) {
+            // nothing behind the first bad record is counted (Parser::each delivers the records before it)
+            const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;
+            first_bad = 4u * pass + fsub;
+            ok = ok && sub < fsub;
+        }
     }
     if (HIST) {
         uint32_t Ls = 0, Lq = 0;
@@ -634,6 +639,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         // the line end this lane writes to the index, and how many records fit a window
         uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0, gmask = 0;
         bool predict = false, flex = false;   // flex: header lengths vary, see flex_pass
+        // a bad record in the LAST range of a shard that ends the stream needs no exact pass: every record in
+        // front of it has been counted, nothing behind it has (tail_x = its offset)
+        // (not with an inferred shard start: that protocol has no classification step behind this kernel)
+        const bool last_eof = rid + 1u == p.n_sranges && (p.flags & F_EOF) && !(p.flags & F_INFER_START) && p.n_avail == p.n_own;
+        unsigned long long tail_x = NONE64;
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
@@ -805,6 +815,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 uint32_t hib;
                 const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
                 const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
+                if (n_win == 0 && last_eof && w.vlen < (uint32_t)C::WIN &&
+                    !(HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
+                    tail_x = cur;    // the stream ends inside this record (or in garbage): the first bad record
+                    break;
+                }
                 if (n_win == 0 || (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
                     failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
                     break;
@@ -822,8 +837,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
                     first_bad = stream_pass<C, HIST>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
-                    failed = true;   // a record that fails validation: the exact path finds and classifies it
-                    break;
+                    if (!last_eof) {
+                        failed = true;   // a record that fails validation: the exact path finds and classifies it
+                        break;
+                    }
+                    n_rec = first_bad;   // the records in front of it stand; the range ends at the bad one
+                    tail_x = (unsigned long long)(w.src + (long long)list[4u * first_bad]);
                 }
                 {
                     const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
@@ -909,6 +928,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             }
             lrank += n_lines;
             cur = w.src + next;
+            if (tail_x != NONE64) break;
             // u16 counter halves: whoever pushes the CTA-wide record count over a multiple of the mark
             // starts a drain epoch; every warp drains its slice when it notices
             if (lane == 0) {
@@ -920,6 +940,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 my_epoch = ep;
                 flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
             }
+        }
+        if (tail_x != NONE64 && !failed) {
+            // (the line ends of the bytes behind it are counted and indexed by fq_tail_index_kernel)
+            if (lane == 0) {
+                atomicMin(&p.res->first_bad, tail_x);
+                p.res->tail_err = 1;
+            }
+            cur = p.n_avail;
         }
         // data that ends inside the owned bytes without a record boundary: not a clean shard
         if (!failed && cur < R1) failed = true;

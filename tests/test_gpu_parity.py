@@ -535,6 +535,23 @@ def test_clean_inputs_stay_on_the_fast_path(torch, oracle, eng, eng300):
     utf8 = b"".join(("@r%d \u00e9\u4e2d" % i).encode() + b"\n" + _rec(i, 150)[_rec(i, 150).index(b"\n") + 1:] for i in range(5000))
     t, n = tiled(utf8, 20)
     assert not path(eng, t, n, False, 5000 * 20)["exact"]          # no histograms: byte values do not matter
+    # an error at the very end of the stream (truncated download, trailing blank lines or garbage) is found and
+    # classified without the exact pass: every record in front of it has been counted, nothing behind it
+    good = oracle.synth_fixed_records(100000).tobytes()
+    for tail in (good[:-1], good[:-200], good + b"\n", good + b"\n" * 50, good + b"@x\nAC\n+\n!\n" + good[:3210],
+                 good + b"garbage without a newline"):
+        ores, ost = oracle.each_stats(tail, 150)
+        assert ores.status != 0
+        d = to_dev(torch, tail)
+        idx = torch.zeros(len(tail) + 8, dtype=torch.int32, device="cuda")
+        for hist in (True, False):
+            eng.parse_device(d, n_own=len(tail), n_avail=len(tail), hist=hist, index=idx)
+            out, st = eng.fetch(want_stats=hist)
+            assert (out.status, out.n_records, out.err_offset) == (ores.status, ores.n_records, ores.err_offset)
+            assert out.n_lines == tail.count(b"\n") and not out.finished
+            assert not eng.last_path()["exact"], (len(tail) - len(good), hist)
+            if hist:
+                assert_stats_equal(st, ost)
 
 
 def test_count_mode_varying_shapes(torch, oracle, eng):
