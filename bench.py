@@ -358,7 +358,7 @@ def run_e2e(args, eng, data, n, world, dev, stream_off):
     res, got = _lib.Result(), ctypes.c_uint64(0)
 
     def step():
-        rc = L.fqb_parse_host(eng.ctx, p, n, _lib.F_HIST | _lib.F_INDEX, ctypes.byref(res), words.ctypes.data,
+        rc = L.fqb_parse_host(eng.ctx, p, n, 0, _lib.F_HIST | _lib.F_INDEX, ctypes.byref(res), words.ctypes.data,
                               pi, n_idx, ctypes.byref(got))
         assert rc == 0 and res.status == 0 and res.n_records == n // REC_BYTES and got.value == n_idx, (rc, res.status)
 

@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libfastq_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
@@ -108,7 +108,7 @@ def lib():
     L.fqb_launch_count.restype = u64
     L.fqb_last_scan_ms.argtypes = [vp]
     L.fqb_last_scan_ms.restype = C.c_float
-    L.fqb_parse_host.argtypes = [vp, vp, u64, u32, C.POINTER(Result), vp, vp, u64, C.POINTER(u64)]
+    L.fqb_parse_host.argtypes = [vp, vp, u64, u64, u32, C.POINTER(Result), vp, vp, u64, C.POINTER(u64)]
     L.fqb_parse_host.restype = i32
     L.fqb_stream_begin.argtypes = [vp, u32]
     L.fqb_stream_begin.restype = i32

@@ -782,13 +782,14 @@ int fqb_stream_finish(fqb_ctx* ctx, fqb_result* res, uint64_t* host_stats)
     return rc;
 }
 
-int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint32_t flags, fqb_result* res,
-                   uint64_t* host_stats, uint32_t* host_index, uint64_t index_cap, uint64_t* n_index)
+int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint64_t stream_offset, uint32_t flags,
+                   fqb_result* res, uint64_t* host_stats, uint32_t* host_index, uint64_t index_cap, uint64_t* n_index)
 {
     if (!ctx || !res || (n && !bytes)) return FQB_E_ARG;
     if ((flags & FQB_F_INDEX) && index_cap && !host_index) return FQB_E_ARG;
     int rc = fqb_stream_begin(ctx, flags);
     if (rc) return rc;
+    ctx->stream_pos = stream_offset;   // offsets reported (and the too-long rule, rec_window()) are stream offsets
     ctx->host_index = host_index;
     ctx->host_index_cap = host_index ? index_cap : 0;
     ctx->stream_partial = (flags & FQB_F_PARTIAL) != 0;

@@ -18,6 +18,15 @@ constexpr int HIST_ROWS = 128;             // byte values with a shared-memory c
 constexpr uint32_t MAXREC = 68u * 1024u;   // src/lib.rs:129 BUFSIZE
 constexpr unsigned long long NONE64 = ~0ull;
 
+// Bytes of the stream the reference can hold of a record that starts at stream offset `off`
+// (src/lib.rs:276-283 + src/buffer.rs:51-100).  With a reader that fills every read() (Cursor, File, &[u8])
+// all buffer refills end on a 16-byte boundary of the STREAM: the first fill is BUFSIZE = 17 * 4096 bytes,
+// clean()/replace_buffer() park the leftover so that it ENDS at a multiple of 16 and read_into() adds a
+// multiple of 4096 (or all of n_free, itself a multiple of 16).  Buffer offsets and stream offsets therefore
+// stay congruent mod 16, an incomplete record is parked at buffer offset `off mod 16`, and "record too long"
+// (n_free() == 0 while still incomplete) is raised iff the record needs more than BUFSIZE - off mod 16 bytes.
+__host__ __device__ inline unsigned long long rec_window(unsigned long long off) { return MAXREC - (off & 15ull); }
+
 constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0x08, F_FRONT16 = 0x10;
 constexpr uint32_t F_INFER_START = 0x20;   // the phase of line_base is unknown: range 0 infers its first record too
 constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad

@@ -121,7 +121,10 @@ __device__ __noinline__ unsigned long long record_global(const ScanParams& p, un
     if (s >= limit) return NONE64;
     const uint8_t* __restrict__ d = p.data;
     const unsigned long long navail = p.n_avail;
-    unsigned long long win_end = s + MAXREC;
+    // the reference's 68 KiB buffer keeps the record at buffer offset (stream offset mod 16) when it refills
+    // (Buffer::clean, src/buffer.rs:51-72: the leftover is parked so that the next read is 16-byte aligned), so
+    // a record fits iff (offset mod 16) + length <= BUFSIZE -- see rec_window()
+    unsigned long long win_end = s + rec_window(p.stream_offset + s);
     const bool window_full = win_end <= navail;
     if (win_end > navail) win_end = navail;
     unsigned long long nl[4] = {0, 0, 0, 0};

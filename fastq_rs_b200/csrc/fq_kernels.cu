@@ -43,7 +43,8 @@ __global__ void fq_diagnose_kernel(const ScanParams p, DevCarry* carry)
     if (s == NONE64) return;
     const uint8_t* d = p.data;
     const unsigned long long avail = p.n_avail - s;
-    const unsigned long long end = s + (avail < MAXREC ? avail : (unsigned long long)MAXREC);
+    const unsigned long long W = rec_window(p.stream_offset + s);   // what the reference's buffer holds of it
+    const unsigned long long end = s + (avail < W ? avail : W);
     int status = 0;
     bool incomplete = false;
     unsigned long long n0, n1 = 0, n2 = 0, n3 = 0;
@@ -71,7 +72,7 @@ __global__ void fq_diagnose_kernel(const ScanParams p, DevCarry* carry)
             if (n3 == NONE64) incomplete = true;
         }
         if (!incomplete && !status) status = (n3 - n2) != (n1 - n0) ? 3 : 51 /* flagged but valid: internal */;
-        if (incomplete) status = avail >= MAXREC ? 4 : 5;
+        if (incomplete) status = avail >= W ? 4 : 5;
     }
     if (lane == 0) {
         r->status = status;

@@ -517,8 +517,9 @@ __device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t 
 struct StreamCta {
     uint32_t n_records, n_bases;   // totals of the CTA (u32: a CTA sees < 4 G bases per launch; native shared atomics)
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
-    uint32_t flush_epoch;
+    uint32_t pad;
 };
+constexpr uint32_t DRAIN_MARK = 24000u;   // records a CTA consumes between two drains of its u16 counter halves
 
 // HIST: the launch accumulates the per-position histograms (FQB_F_HIST); the two variants share no
 // hot code (rounds + '\n'-row check vs. newline count), so each is compiled without the other's registers
@@ -546,7 +547,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         cta.n_records = 0;
         cta.n_bases = 0;
         cta.recs = 0;
-        cta.flush_epoch = 0;
     }
     fence_mbar_init();
     __syncthreads();
@@ -583,8 +583,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
 
     unsigned long long cur = 0, lrank = 0;
     bool failed = false;
-    uint32_t my_epoch = 0;
-    constexpr int SLICE = (C::HIST_WORDS + C::NWARPS - 1) / C::NWARPS;
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
@@ -929,16 +927,19 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             lrank += n_lines;
             cur = w.src + next;
             if (tail_x != NONE64) break;
-            // u16 counter halves: whoever pushes the CTA-wide record count over a multiple of the mark
-            // starts a drain epoch; every warp drains its slice when it notices
-            if (lane == 0) {
-                const uint32_t before = atomicAdd(&cta.recs, n_rec);
-                if (before / 24000u != (before + n_rec) / 24000u) atomicAdd(&cta.flush_epoch, 1u);
-            }
-            const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(&cta.flush_epoch);
-            if (ep != my_epoch) {
-                my_epoch = ep;
-                flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
+            // u16 counter halves: the warp that pushes the CTA-wide record count over a multiple of the mark
+            // drains the WHOLE table, there and then (lock-free: atomicExch leaves the other warps' concurrent
+            // bumps intact).  The drain does not depend on any other warp still being inside its range loop --
+            // warps that have finished (or never were live) take no part in it -- so between two drains of a
+            // counter the CTA consumes at most DRAIN_MARK records plus the few thousand it gets through while
+            // one warp walks the table (~20 K words): far below 65 535 per half, whatever the input looks like.
+            if (HIST) {
+                uint32_t trip = 0;
+                if (lane == 0) {
+                    const uint32_t before = atomicAdd(&cta.recs, n_rec);
+                    trip = before / DRAIN_MARK != (before + n_rec) / DRAIN_MARK ? 1u : 0u;
+                }
+                if (__shfl_sync(0xffffffffu, trip, 0)) flush_hist<C>(hist, p, 0, C::HIST_WORDS, lane, 32);
             }
         }
         if (tail_x != NONE64 && !failed) {

@@ -212,11 +212,12 @@ class Engine:
 
     # ---- host path -------------------------------------------------------------------------
     def parse_host(self, data, *, hist: bool = True, want_index: bool = False, want_stats: bool = True,
-                   partial: bool = False):
+                   partial: bool = False, stream_offset: int = 0):
         """Delimit (+histograms) host bytes end to end through the pinned ring.
         `data`: bytes-like / uint8 ndarray / (address, nbytes).  Returns (Outcome, Stats|None, index|None)
         where index = u64 stream offsets of every line end.  `partial`: one refill of a longer stream
-        (FQB_F_PARTIAL): an incomplete trailing record is reported in Outcome.tail_offset, not as an error."""
+        (FQB_F_PARTIAL): an incomplete trailing record is reported in Outcome.tail_offset, not as an error.
+        `stream_offset`: stream offset of data[0] (all offsets that come back are stream offsets)."""
         if isinstance(data, tuple):
             addr, n = data
             keep = None
@@ -230,10 +231,10 @@ class Engine:
         n_idx = C.c_uint64(0)
         flags = (F_HIST if hist else 0) | (F_INDEX if want_index else 0) | (F_PARTIAL if partial else 0)
         _check(self.ctx, self.L.fqb_parse_host(
-            self.ctx, addr, n, flags, C.byref(res), words.ctypes.data if want_stats else None,
+            self.ctx, addr, n, stream_offset, flags, C.byref(res), words.ctypes.data if want_stats else None,
             idx.ctypes.data if want_index else None, idx.size if want_index else 0, C.byref(n_idx)),
             "fqb_parse_host")
-        index = expand_index(idx[:n_idx.value]) if want_index else None
+        index = expand_index(idx[:n_idx.value], stream_offset) if want_index else None
         return self._outcome(res), (Stats(self.max_len, words) if want_stats else None), index
 
     # ---- streaming ring (thread_reader protocol) -------------------------------------------
@@ -280,12 +281,13 @@ class Engine:
         return out, total
 
 
-def expand_index(lo32: np.ndarray) -> np.ndarray:
+def expand_index(lo32: np.ndarray, base: int = 0) -> np.ndarray:
     """Low-32-bit line-end offsets -> u64 stream offsets (offsets are strictly increasing, so a
-    decrease marks a 4 GiB wrap)."""
-    lo = lo32.astype(np.uint64)
-    if lo.size == 0:
-        return lo
+    decrease marks a 4 GiB wrap).  `base`: stream offset the first entries lie behind (< 4 GiB before them)."""
+    if lo32.size == 0:
+        return lo32.astype(np.uint64)
+    rel = (lo32 - np.uint32(base & 0xFFFFFFFF)).astype(np.uint32)      # offsets relative to base, mod 2^32
+    lo = rel.astype(np.uint64)
     wraps = np.zeros(lo.size, dtype=np.uint64)
-    wraps[1:] = np.cumsum(lo32[1:] < lo32[:-1]).astype(np.uint64)
-    return lo + (wraps << np.uint64(32))
+    wraps[1:] = np.cumsum(rel[1:] < rel[:-1]).astype(np.uint64)
+    return lo + (wraps << np.uint64(32)) + np.uint64(base)

@@ -174,7 +174,7 @@ class _Delimited:
     def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray, base: int = 0, delivered: int = 0):
         self.base, self.delivered = base, delivered
         n = outcome.n_records
-        ends = index[:4 * n].astype(np.int64).reshape(n, 4)
+        ends = index[:4 * n].astype(np.int64).reshape(n, 4) - base     # relative to data[0]
         starts = np.empty(n, dtype=np.int64)
         if n:
             starts[0] = 0
@@ -185,7 +185,48 @@ class _Delimited:
     def raise_for_status(self) -> None:
         o = self.outcome
         if o.status != 0:
-            raise FastqError(o.status, self.base + o.err_offset, self.delivered + o.n_records)
+            raise FastqError(o.status, o.err_offset, self.delivered + o.n_records)   # (stream offset)
+
+
+class _SyncChannel:
+    """std::sync::mpsc::sync_channel(bound) as parallel_each uses it (src/lib.rs:522): a bounded queue whose
+    send() blocks while it is full and FAILS once the receiver is gone; the receiver's iterator ends when
+    the sender is dropped and the queue is empty."""
+    _END = object()
+
+    def __init__(self, bound: int):
+        self._q: queue.Queue = queue.Queue(maxsize=bound)
+        self._rx_gone = threading.Event()
+        self._closed = False
+
+    def send(self, item) -> bool:
+        while not self._rx_gone.is_set():
+            try:
+                self._q.put(item, timeout=0.02)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def close(self) -> None:            # drop(tx)
+        if not self._closed:
+            self._closed = True
+            self.send(self._END)
+
+    def receive(self):
+        while True:
+            item = self._q.get()
+            if item is self._END:
+                return
+            yield item
+
+    def hang_up(self) -> None:          # drop(rx)
+        self._rx_gone.set()
+        try:
+            while True:
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
 
 
 class RecordRefIter:  # src/lib.rs:241-304
@@ -241,11 +282,11 @@ class Parser:
             eof = n < ch
             buf = buf[:left.size + n]
             outcome, _, index = eng.parse_host(buf, hist=False, want_index=True, want_stats=False,
-                                               partial=not eof)
+                                               partial=not eof, stream_offset=base)
             yield _Delimited(buf, outcome, index, base, delivered)
             if eof or outcome.status != 0:
                 return
-            t = buf.size if outcome.tail_offset is None else outcome.tail_offset
+            t = buf.size if outcome.tail_offset is None else outcome.tail_offset - base
             left, base, delivered = buf[t:], base + t, delivered + outcome.n_records
 
     def ref_iter(self) -> RecordRefIter:
@@ -281,32 +322,22 @@ class Parser:
             d.raise_for_status()
 
     def parallel_each(self, n_threads: int, func: Callable[[Iterator[RecordSet]], object]) -> list:
-        """n_threads workers, each fed RecordSets round-robin over a bounded queue of 10
+        """n_threads workers, each fed RecordSets round-robin over a bounded channel of 10
         (src/lib.rs:509-566).  Returns the workers' results in worker order; raises FastqError on
-        bad input (after joining the workers)."""
-        queues = [queue.Queue(maxsize=10) for _ in range(n_threads)]
+        bad input (after joining the workers).  A worker that returns before its iterator is exhausted
+        hangs up its channel: the producer's next send to it fails and the producer stops, as in the
+        reference (src/lib.rs:540-542, doc-test "Early return stops the parser" :484)."""
+        chans = [_SyncChannel(10) for _ in range(n_threads)]
         results: list = [None] * n_threads
         errors: list = [None] * n_threads
-        DONE = object()
 
         def worker(i):
-            def sets():
-                while True:
-                    s = queues[i].get()
-                    if s is DONE:
-                        return
-                    yield s
             try:
-                results[i] = func(sets())
+                results[i] = func(chans[i].receive())
             except BaseException as e:  # worker panic -> re-raised on join (src/lib.rs:558)
                 errors[i] = e
             finally:
-                while True:  # drain so the producer never blocks on a dead worker
-                    try:
-                        if queues[i].get_nowait() is DONE:
-                            break
-                    except queue.Empty:
-                        break
+                chans[i].hang_up()      # rx dropped: pending and future sends fail
 
         threads = [threading.Thread(target=worker, args=(i,), name=f"worker-{i}") for i in range(n_threads)]
         for t in threads:
@@ -315,11 +346,16 @@ class Parser:
         try:
             if n_threads:
                 for k, s in enumerate(self.record_sets()):
-                    queues[k % n_threads].put(s)
+                    if not chans[k % n_threads].send(s):
+                        break           # the worker quit: stop parsing (src/lib.rs:540-542)
         except FastqError as e:
             err = e
-        for q in queues:
-            q.put(DONE)
+        except BaseException:
+            for c in chans:
+                c.close()
+            raise
+        for c in chans:
+            c.close()                   # drop(senders): the workers' iterators end (src/lib.rs:551)
         for t in threads:
             t.join()
         for e in errors:

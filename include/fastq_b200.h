@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FQB_ABI_VERSION 2u
+#define FQB_ABI_VERSION 3u
 
 /* ---- status codes --------------------------------------------------------------------
  * 1..5 are the reference's grammar errors; the host shim maps each to
@@ -42,8 +42,16 @@ enum {
     FQB_E_CUDA = 100     /* CUDA runtime failure; fqb_last_error() has the text */
 };
 
-/* The reference refuses records that do not fit its 68 KiB window (src/lib.rs:129,278-283).
- * Here: a record (start '@' .. final '\n' inclusive) longer than this is FQB_E_TOO_LONG. */
+/* The reference refuses records that do not fit its 68 KiB window (src/lib.rs:129,278-283).  Whether a
+ * record of 69 617 .. 69 632 bytes fits depends on where Buffer::clean parks the incomplete record
+ * (src/buffer.rs:51-72: so that the next read is 16-byte aligned).  With a reader that fills every read()
+ * (Cursor, File, &[u8] -- the readers of the reference's own tests) every refill ends on a 16-byte boundary
+ * of the stream, the record is parked at buffer offset (stream offset mod 16), and the rule is exact:
+ *     a record starting at stream offset p fits  iff  (p mod 16) + length <= FQB_MAX_RECORD_BYTES;
+ *     an incomplete record is FQB_E_TOO_LONG iff the stream holds >= FQB_MAX_RECORD_BYTES - (p mod 16)
+ *     bytes from p on, else FQB_E_TRUNCATED.
+ * That is the rule implemented here (tests/test_gpu_parity.py::test_too_long_band checks it against the
+ * oracle's restatement of Buffer); the stream offsets of the shards / chunks therefore matter mod 16. */
 #define FQB_MAX_RECORD_BYTES (68u * 1024u)
 
 /* ---- flags for fqb_shard.flags -------------------------------------------------------- */
@@ -191,10 +199,11 @@ int fqb_fetch_filter(fqb_ctx *ctx, void *stream, uint64_t *n_kept, uint64_t *out
  * before the first bad record, up to index_cap entries; *n_index = entries written.  A host_index in
  * pinned memory (fqb_host_alloc) is written by the device in stream order, with no synchronisation
  * per chunk; pageable memory costs one per chunk.
+ * stream_offset: stream offset of bytes[0]; err_offset, tail_offset and the index are stream offsets.
  * flags: FQB_F_HIST | FQB_F_INDEX | FQB_F_PARTIAL.  With FQB_F_PARTIAL the call is one refill of a
- * longer stream (bounded-memory each()/record_sets(): src/lib.rs:262-294, 364-425): offsets are
- * relative to `bytes`, which must start at a record start. */
-int fqb_parse_host(fqb_ctx *ctx, const uint8_t *bytes, uint64_t n, uint32_t flags,
+ * longer stream (bounded-memory each()/record_sets(): src/lib.rs:262-294, 364-425): `bytes` must
+ * start at a record start. */
+int fqb_parse_host(fqb_ctx *ctx, const uint8_t *bytes, uint64_t n, uint64_t stream_offset, uint32_t flags,
                    fqb_result *res, uint64_t *host_stats,
                    uint32_t *host_index, uint64_t index_cap, uint64_t *n_index);
 

@@ -111,3 +111,31 @@ class FakeEngine:
             _, st = oracle.each_stats(buf[s:end].tobytes(), self.max_len)
             self._stats[:] = torch.from_numpy(stats_words(self.max_len, st, n_rec).view(np.int64))
         self._publish(Outcome(status, status == 0, n_rec, n_lines, err, None, phase))
+
+
+class FakeHostEngine:
+    """Oracle-backed stand-in for the HOST entry points of fastq_rs_b200.Engine (parse_host with
+    FQB_F_PARTIAL refills), so that the host mirror of the crate's drivers (fastq_rs_b200/parser.py: each,
+    record_sets, parallel_each, each_zipped) can be tested without a GPU.  TEST INFRASTRUCTURE."""
+
+    def __init__(self, max_len=150):
+        self.max_len = max_len
+        self.n_calls = 0
+
+    def parse_host(self, data, *, hist=True, want_index=False, want_stats=True, partial=False, stream_offset=0):
+        self.n_calls += 1
+        buf = bytes(np.ascontiguousarray(data).view(np.uint8).tobytes()) if isinstance(data, np.ndarray) else bytes(data)
+        # the too-long rule depends on the stream offset mod 16: put a record of that length (mod 16) in front
+        lead = 16 + (stream_offset & 15)
+        pre = b"@" + b"a" * (lead - 8) + b"\nA\n+\nB\n"
+        res, idx = oracle.each_index(pre + buf)
+        n = res.n_records - 1
+        status, err, tail = res.status, res.err_offset - lead + stream_offset, None
+        if partial and status == oracle.E_TRUNCATED:
+            status, tail, err = 0, err, 0          # the refill ends inside a record: carried over, not an error
+        index = (idx[1:, 1:5].reshape(-1).astype(np.int64) - lead + stream_offset).astype(np.uint64)
+        out = Outcome(status, status == 0 and tail is None, n, buf.count(b"\n"), err if status else 0, tail, 0)
+        st = None
+        if want_stats:
+            _, st = oracle.each_stats(buf, self.max_len)
+        return out, st, (index if want_index else None)

@@ -35,7 +35,8 @@ def test_library_exports_every_declared_symbol(so_path):
     for name in header_functions():
         assert hasattr(L, name), name
     L.fqb_abi_version.restype = C.c_uint32
-    assert L.fqb_abi_version() == 2
+    from fastq_rs_b200 import _lib
+    assert L.fqb_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_torch_types_in_signatures():

@@ -249,6 +249,106 @@ def test_record_at_size_limit(torch, oracle, eng):
     assert out.status == 4
 
 
+def _rec_total(n: int) -> bytes:
+    """a valid record of exactly n >= 8 bytes (all of its length in the id line)"""
+    return b"@" + b"a" * (n - 8) + b"\nA\n+\nB\n"
+
+
+TOO_LONG_FIRST = [[], [8], [9], [15], [16], [17], [31], [45], [8, 9], [1000, 13], [69000], [40000, 40000, 11]]
+
+
+@pytest.mark.parametrize("first", TOO_LONG_FIRST, ids=lambda f: "+".join(map(str, f)) or "start")
+def test_too_long_band(first, torch, oracle, eng, fq):
+    """Records of 69 610 .. 69 640 bytes: whether the reference accepts one depends on where Buffer::clean parks
+    it (src/buffer.rs:51-72, src/lib.rs:276-283), i.e. on the stream offset mod 16 of its first byte.  Expected
+    values come from the oracle's restatement of Buffer; every length goes through fqb_parse_device,
+    fqb_parse_host and the FQB_F_PARTIAL refill path."""
+    pre = b"".join(_rec_total(n) for n in first)
+    for L in list(range(69610, 69641)):
+        data = pre + _rec_total(L) + _rec_total(20)
+        ores, _ = oracle.each_index(data)
+        fits = (len(pre) & 15) + L <= 68 * 1024
+        assert (ores.status, ores.n_records) == ((0, len(first) + 2) if fits else (4, len(first))), (first, L)
+        t = to_dev(torch, data)
+        eng.parse_device(t, n_own=len(data), n_avail=len(data), hist=False)
+        out, _ = eng.fetch(want_stats=False)
+        assert (out.status, out.n_records) == (ores.status, ores.n_records), (first, L, out)
+        if ores.status:
+            assert out.err_offset == ores.err_offset
+        if L % 5 == 0 or not fits:
+            hout, _, _ = eng.parse_host(data, hist=False, want_stats=False)
+            assert (hout.status, hout.n_records) == (ores.status, ores.n_records), (first, L, hout)
+            seen = []
+            try:
+                fq.Parser(io.BytesIO(data), engine=eng, chunk_bytes=50000).each(lambda r: seen.append(r.offset) or True)
+                assert ores.status == 0
+            except fq.FastqError as e:
+                assert (e.status, e.offset, e.n_delivered) == (ores.status, ores.err_offset, ores.n_records)
+            assert len(seen) == ores.n_records, (first, L)
+    # a record that never ends: too long iff the stream holds the whole window from its start, else truncated
+    for avail in (69610, 69616, 69617, 69620, 69625, 69631, 69632, 69633, 69640):
+        data = pre + b"@" + b"a" * (avail - 1)
+        ores, _ = oracle.each_index(data)
+        assert ores.status == (4 if avail >= 68 * 1024 - (len(pre) & 15) else 5)
+        t = to_dev(torch, data)
+        eng.parse_device(t, n_own=len(data), n_avail=len(data), hist=False)
+        out, _ = eng.fetch(want_stats=False)
+        assert (out.status, out.n_records, out.err_offset) == (ores.status, ores.n_records, ores.err_offset), (first, avail)
+        hout, _, _ = eng.parse_host(data, hist=False, want_stats=False)
+        assert (hout.status, hout.n_records, hout.err_offset) == (ores.status, ores.n_records, ores.err_offset)
+
+
+def test_too_long_band_in_a_later_shard(torch, oracle, eng):
+    """the rule uses the STREAM offset of the record: a shard that starts at a nonzero stream offset"""
+    for shift in (0, 5, 16, 27):
+        pre = _rec_total(32 + shift)
+        for L in (69616, 69617, 69620, 69627, 69632):
+            data = pre + _rec_total(L) + _rec_total(20)
+            ores, _ = oracle.each_index(data)
+            body = data[len(pre):]
+            t = to_dev(torch, body)
+            eng.parse_device(t, n_own=len(body), n_avail=len(body), hist=False, stream_offset=len(pre), line_base=4)
+            out, _ = eng.fetch(want_stats=False)
+            assert (out.status, out.n_records + 1) == (ores.status, ores.n_records), (shift, L)   # (+ the record in front)
+            if ores.status:
+                assert out.err_offset == ores.err_offset
+
+
+def test_histogram_drain_with_uneven_warps(torch, oracle, eng):
+    """The u16 counter halves of the speculative kernel are drained by whichever warp pushes the CTA's record
+    count over the mark -- independent of the other warps still being at work.  Here one warp range in 32 (the
+    range whose slice of the table holds ('A', 0) and ('I', 0) under a per-warp drain) holds 2 KiB records and is
+    done early, while the other 31 ranges of its CTA keep bumping those two counters 8192 times each: > 250 000
+    bumps per CTA on one counter word."""
+    blk = 65536
+    small = b"@\nA\n+\nI\n" * (blk // 8)
+    rng = np.random.default_rng(5)
+    long_recs = []
+    for i in range(blk // 2048):
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 1020))
+        qual = bytes(rng.integers(40, 70, 1020, dtype=np.uint8))
+        long_recs.append(b"@hh\n" + seq + b"\n+\n" + qual + b"\n")
+    long_blk = b"".join(long_recs)
+    assert len(small) == blk and len(long_blk) == blk
+    n_ranges = 148 * 32
+    cta = torch.cat([torch.from_numpy(np.frombuffer(long_blk if w == 3 else small, dtype=np.uint8).copy()) for w in range(32)]).cuda()
+    t = torch.cat([cta.repeat(n_ranges // 32), torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    n = blk * n_ranges
+    eng.parse_device(t, n_own=n, n_avail=n, hist=True)
+    out, st = eng.fetch()
+    n_small, n_long = (n_ranges - n_ranges // 32) * (blk // 8), (n_ranges // 32) * (blk // 2048)
+    assert out.status == 0 and out.n_records == n_small + n_long
+    assert not eng.last_path()["exact"]
+    _, s_small = oracle.each_stats(small, 150)
+    _, s_long = oracle.each_stats(long_blk, 150)
+    k_small, k_long = n_ranges - n_ranges // 32, n_ranges // 32
+    np.testing.assert_array_equal(st.qual_hist, s_small.qual_hist * k_small + s_long.qual_hist * k_long)
+    np.testing.assert_array_equal(st.base_hist, s_small.base_hist * k_small + s_long.base_hist * k_long)
+    np.testing.assert_array_equal(st.len_hist, s_small.len_hist * k_small + s_long.len_hist * k_long)
+    assert st.n_bases == s_small.n_bases * k_small + s_long.n_bases * k_long
+    assert st.clip_seq == s_long.clip_seq * k_long and st.clip_qual == s_long.clip_qual * k_long
+
+
 def test_dense_newlines_list_overflow(torch, oracle, eng):
     # > LIST_CAP newlines in one 16 KiB tile: 6-byte records (empty seq/qual) and 8-byte records
     data = b"@\n\n+\n\n" * 6000 + b"@a\nA\n+\n!\n" * 3000 + b"@\n\n+\n\n" * 100
@@ -793,7 +893,7 @@ def test_parse_host_pinned_index(fq, oracle):
             assert L.fqb_host_alloc(cap * 4, ctypes.byref(p)) == 0
             res, got = _lib.Result(), ctypes.c_uint64(0)
             a = np.frombuffer(data, dtype=np.uint8)
-            rc = L.fqb_parse_host(e.ctx, a.ctypes.data if a.size else None, a.size, _lib.F_INDEX, ctypes.byref(res), None,
+            rc = L.fqb_parse_host(e.ctx, a.ctypes.data if a.size else None, a.size, 0, _lib.F_INDEX, ctypes.byref(res), None,
                                   p, cap, ctypes.byref(got))
             assert rc == 0 and (res.status, res.n_records) == (ores.status, ores.n_records)
             idx = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), shape=(cap,))

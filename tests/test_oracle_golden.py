@@ -257,3 +257,31 @@ def test_fuzz_oracle_vs_pymodel(data, cfg):
     # index form
     _r, idx = oracle.each_index(data, bufsize=bufsize, max_read=max_read)
     assert [int(x) for x in idx[:, 0]] == [r.offset for r in recs]
+
+
+def _rec_total(n: int) -> bytes:
+    return b"@" + b"a" * (n - 8) + b"\nA\n+\nB\n"
+
+
+@pytest.mark.parametrize("first", [[], [8], [15], [16], [45], [1000, 13], [69000], [40000, 40000, 11]],
+                         ids=lambda f: "+".join(map(str, f)) or "start")
+def test_too_long_band_closed_form(first):
+    """The closed form the CUDA path implements for "Fastq record is too long" (include/fastq_b200.h:
+    a record at stream offset p fits iff (p mod 16) + length <= BUFSIZE; an incomplete one is too long iff the
+    stream holds BUFSIZE - p mod 16 bytes from p on, else truncated) against the oracle's restatement of
+    Buffer::clean / read_into / RecordRefIter::advance (src/buffer.rs:51-100, src/lib.rs:255-303), for a reader
+    that fills every read -- and the pure-Python model agrees on a subset."""
+    BUF = 68 * 1024
+    pre = b"".join(_rec_total(n) for n in first)
+    p = len(pre)
+    for L in range(69605, 69645):
+        data = pre + _rec_total(L) + _rec_total(20)
+        res, _ = oracle.each_index(data)
+        fits = (p & 15) + L <= BUF
+        assert (res.status, res.n_records) == ((0, len(first) + 2) if fits else (4, len(first))), (first, L)
+        if L in (69616, 69617, 69625, 69632, 69633):
+            st_m, recs_m = pymodel.each(data)
+            assert (st_m, len(recs_m)) == (res.status, res.n_records)
+    for avail in range(69605, 69645):
+        res, _ = oracle.each_index(pre + b"@" + b"a" * (avail - 1))
+        assert (res.status, res.n_records) == (4 if avail >= BUF - (p & 15) else 5, len(first)), (first, avail)

@@ -20,7 +20,7 @@ res = _lib.Result(); got = ctypes.c_uint64(0)
 for flags, name in ((_lib.F_HIST, "hist, no index"), (_lib.F_INDEX, "index only"), (_lib.F_HIST | _lib.F_INDEX, "hist + index")):
     for r in range(3):
         t0 = time.perf_counter()
-        rc = L.fqb_parse_host(eng.ctx, p, n, flags, ctypes.byref(res), None, pi if flags & _lib.F_INDEX else None,
+        rc = L.fqb_parse_host(eng.ctx, p, n, 0, flags, ctypes.byref(res), None, pi if flags & _lib.F_INDEX else None,
                               n_idx if flags & _lib.F_INDEX else 0, ctypes.byref(got))
         dt = time.perf_counter() - t0
         assert rc == 0 and res.status == 0 and res.n_records == n // 321, (rc, res.status)
