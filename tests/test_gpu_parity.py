@@ -317,16 +317,16 @@ def test_too_long_band_in_a_later_shard(torch, oracle, eng):
 def test_histogram_drain_with_uneven_warps(torch, oracle, eng):
     """The u16 counter halves of the speculative kernel are drained by whichever warp pushes the CTA's record
     count over the mark -- independent of the other warps still being at work.  Here one warp range in 32 (the
-    range whose slice of the table holds ('A', 0) and ('I', 0) under a per-warp drain) holds 2 KiB records and is
+    range whose slice of the table holds ('A', 0) and ('I', 0) under a per-warp drain) holds 1 KiB records and is
     done early, while the other 31 ranges of its CTA keep bumping those two counters 8192 times each: > 250 000
     bumps per CTA on one counter word."""
     blk = 65536
     small = b"@\nA\n+\nI\n" * (blk // 8)
     rng = np.random.default_rng(5)
     long_recs = []
-    for i in range(blk // 2048):
-        seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 1020))
-        qual = bytes(rng.integers(40, 70, 1020, dtype=np.uint8))
+    for i in range(blk // 1024):
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 508))
+        qual = bytes(rng.integers(40, 70, 508, dtype=np.uint8))
         long_recs.append(b"@hh\n" + seq + b"\n+\n" + qual + b"\n")
     long_blk = b"".join(long_recs)
     assert len(small) == blk and len(long_blk) == blk
@@ -336,7 +336,7 @@ def test_histogram_drain_with_uneven_warps(torch, oracle, eng):
     n = blk * n_ranges
     eng.parse_device(t, n_own=n, n_avail=n, hist=True)
     out, st = eng.fetch()
-    n_small, n_long = (n_ranges - n_ranges // 32) * (blk // 8), (n_ranges // 32) * (blk // 2048)
+    n_small, n_long = (n_ranges - n_ranges // 32) * (blk // 8), (n_ranges // 32) * (blk // 1024)
     assert out.status == 0 and out.n_records == n_small + n_long
     assert not eng.last_path()["exact"]
     _, s_small = oracle.each_stats(small, 150)
