@@ -10,8 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfastq_b200.so")
-ABI_VERSION = 3
+SO_PATH = os.environ.get("FQB_LIB") or os.path.join(_HERE, "libfastq_b200.so")   # FQB_LIB: A/B builds (tools/)
+ABI_VERSION = int(os.environ.get("FQB_ABI", "3"))   # (FQB_ABI: A/B runs against an older build, tools/)
 
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)

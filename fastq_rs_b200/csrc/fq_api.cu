@@ -20,8 +20,53 @@ using namespace fq;
 
 namespace {
 
-__global__ void fq_init_kernel(DevResult* r, int spec_fail, int line_phase)
+// Reset of the device-resident outcome + a look at the head of the shard (one warp): do its reads vary in
+// length?  The first PROBE_BYTES are cut into lines; with the strict 4-line cadence (src/records.rs:201-247)
+// line j and line j + 4 belong to the same kind of line whatever the phase, so on fixed-length reads at least
+// three of the four kinds keep their length from record to record (the id line may vary: instrument
+// coordinates).  If two or more kinds vary, the launch goes to the speculative kernel's variable-length
+// variant -- and so does a shard whose head holds bytes >= 0x80.  A hint only: either variant delivers the
+// exact result on any input.
+constexpr int PROBE_BYTES = 8192, PROBE_LINES = 256;
+__global__ void __launch_bounds__(32) fq_init_kernel(DevResult* r, int spec_fail, int line_phase, const uint8_t* data,
+                                                     unsigned long long n, int probe)
 {
+    __shared__ unsigned short pos[PROBE_LINES + 1];
+    const int lane = threadIdx.x;
+    int shape_var = 0;
+    if (probe && n >= (unsigned long long)PROBE_BYTES) {
+        // newline positions of the first PROBE_BYTES, in order: 256 bytes per lane, warp prefix of the counts
+        const uint8_t* d = data + lane * (PROBE_BYTES / 32);
+        int c = 0;
+        unsigned hi = 0;
+        for (int i = 0; i < PROBE_BYTES / 32; ++i) {
+            c += d[i] == '\n';
+            hi |= d[i];
+        }
+        int incl = c;
+        for (int k = 1; k < 32; k <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += v;
+        }
+        int rank = incl - c;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int i = 0; i < PROBE_BYTES / 32 && rank < PROBE_LINES; ++i)
+            if (d[i] == '\n') pos[rank++] = (unsigned short)(lane * (PROBE_BYTES / 32) + i);
+        __syncwarp();
+        const int nl = total < PROBE_LINES ? total : PROBE_LINES;
+        // line j = (pos[j], pos[j + 1]]; compare the lengths of line j and line j + 4
+        unsigned varies = 0;                                     // bit k: some line of kind k changed its length
+        for (int j = lane; j + 5 < nl; j += 32)
+            if (pos[j + 1] - pos[j] != pos[j + 5] - pos[j + 4]) varies |= 1u << (j & 3);
+        varies = __reduce_or_sync(0xffffffffu, varies);
+        shape_var = (nl >= 16 && __popc(varies) >= 2) ? 1 : 0;
+        // bytes >= 0x80 (UTF-8 in the id lines, say): the predicting variant leaves the fast path at the first
+        // window it has to scan that holds one; the variable-length variant only minds them in the sequence and
+        // quality lines themselves
+        if (__any_sync(0xffffffffu, (hi & 0x80u) != 0)) shape_var = 1;
+    }
+    if (lane != 0) return;
+    r->shape_var = shape_var;
     r->first_bad = NONE64;
     r->tail_start = NONE64;
     r->n_lines = 0;
@@ -346,7 +391,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 1, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3));
+    fq_init_kernel<<<1, 32, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3), sh->d_bytes, sh->n_avail,
+                                     (fast && (sh->flags & FQB_F_HIST) && !getenv("FQB_NO_VAR")) ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
@@ -359,7 +405,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             CK(launch_stream(p, ctx->nchunk, ctx->grid, st));
             if (timed) CK(cudaEventRecord(ctx->ev1, st));
             CK(launch_stream_verify(p, carry, st));
-            ctx->launches += 2;
+            ctx->launches += (p.flags & F_HIST) ? 3 : 2;
         }
         // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
         // of the CTA ranges -> exact line numbers -> exact kernel.  It needs the exact line_base: with

@@ -48,7 +48,9 @@ struct DevResult {
     unsigned long long n_win_pred;  // windows of the speculative kernel that were predicted / scanned (FQB_DEBUG)
     unsigned long long n_win_scan;
     int tail_err;                   // the speculative kernel itself found the first bad record: it lies in the last
-    int pad2;                       // range of an EOF shard, so nothing behind it was counted; first_bad holds it
+    int shape_var;                  // range of an EOF shard, so nothing behind it was counted; first_bad holds it
+                                    // shape_var: the head of the shard holds reads of varying length (fq_init_kernel):
+                                    // the speculative kernel's variant for such input does the work
 };
 
 // one contiguous range of tiles = the work of one CTA

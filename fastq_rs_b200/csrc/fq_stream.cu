@@ -35,13 +35,14 @@
 
 namespace fq {
 
-template <int NCHUNK_, int NWARPS_, int WIN_>
+template <int NCHUNK_, int NWARPS_, int WIN_, int SPARE_ROW_ = 0>
 struct SCfg {
     static constexpr int NCHUNK = NCHUNK_;
     static constexpr int NWARPS = NWARPS_;                 // autonomous warps per CTA
     static constexpr int NTHREADS = 32 * NWARPS_;
     static constexpr int PPAD = 32 * NCHUNK;
-    static constexpr int CHUNK_WORDS = HIST_ROWS * 32;
+    // 128 byte rows (+ a spare row in the variable-length variant, see mask_to_trash)
+    static constexpr int CHUNK_WORDS = (HIST_ROWS + SPARE_ROW_) * 32;
     static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
     static constexpr int WIN = WIN_;                       // window bytes (a multiple of 512)
@@ -141,11 +142,11 @@ __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, un
 //   list[0] = cursor, list[j] = position after the j-th '\n' of [pad, vlen)
 // The ranks need no second pass: the running count is warp-local.  Per 512-byte unit the per-lane
 // counts (0, 1, rarely 2) are prefix-summed with two ballots; a piece with three or more newlines
-// sends the unit through the generic path.  Returns the newline count; hib = OR of all words.
+// sends the unit through the generic path.  Returns the newline count; HIB: hib = OR of all words.
 // RAGGED: the window is shorter than WIN (the end of the shard) -- stale bytes are masked out.
-template <class C, bool RAGGED>
-__device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib,
-                                               int lane, uint32_t lt_mask)
+template <class C, bool RAGGED, bool HIB>
+__device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib, int lane,
+                                               uint32_t lt_mask)
 {
     const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
     const uint32_t list_s = buf_s + (uint32_t)(C::WIN + 16);
@@ -157,7 +158,7 @@ __device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, c
     for (int it = 0; it < C::NU; ++it) {
         const uint32_t off = (uint32_t)it * UNIT + (uint32_t)lane * 16u;
         const uint4 v = lds_v4(buf_s + off);
-        hib |= v.x | v.y | v.z | v.w;
+        if (HIB) hib |= v.x | v.y | v.z | v.w;
         uint32_t mm = nlmask16k(v, kA, kB);                                 // bit 7 + i = byte i of the piece
         if (it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
         if (RAGGED) {                                                       // stale bytes beyond the data
@@ -192,12 +193,12 @@ __device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, c
     return ubase - 1u;
 }
 
-template <class C>
-__device__ __forceinline__ uint32_t win_scan(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib,
-                                             int lane, uint32_t lt_mask)
+template <class C, bool HIB>
+__device__ __forceinline__ uint32_t win_scan(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib, int lane,
+                                             uint32_t lt_mask)
 {
-    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true>(buf_s, list, w, hib, lane, lt_mask);
-    return win_scan_t<C, false>(buf_s, list, w, hib, lane, lt_mask);
+    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true, HIB>(buf_s, list, w, hib, lane, lt_mask);
+    return win_scan_t<C, false, HIB>(buf_s, list, w, hib, lane, lt_mask);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,6 +411,144 @@ __device__ __forceinline__ uint32_t stream_pass(const ScanParams& p, const uint8
 }
 
 // ------------------------------------------------------------------------------------------
+// SCANNED windows: records of any shape, delimited by the scan's list.
+//   validate_block  lane j <-> record j of the window (32 at a time): '@' / '+' / raw-length validation
+//                   (src/records.rs:201-247), '\r' trim, totals, length histogram -- all lane-parallel
+//   line_steps      then ONE record at a time for the whole warp: lanes 0..15 take the sequence line, lanes
+//                   16..31 the quality line, 4 bytes per lane and step = 64 positions of both lines per step.
+//                   Reads of any length keep all lanes busy up to the last step of each record (no waiting
+//                   for the longest of four records as with 8 lanes per record), and only that last step
+//                   is guarded.  Bank = position % 32 as everywhere: lane (sub = lane >> 3, i = lane & 7)
+//                   visits byte (k + sub) & 3 of its word in its k-th bump, so the 32 lanes of every ATOMS hit
+//                   32 different banks (the two halves use the lo / hi half of the same counters).
+// ------------------------------------------------------------------------------------------
+struct StepK {    // per-lane constants of line_steps (made once per stretch of variable-shape windows)
+    uint32_t lane_base;    // buf_s + 4 * (lane & 15)
+    uint32_t lane_pos;     // 4 * (lane & 15): position of this lane's word in step 0
+    uint32_t inc;          // 1 for the sequence half, 0x10000 for the quality half
+    uint32_t hk[4];        // shared address of hist[chunk of the lane's word in step 0][0][position visited k-th]
+    uint32_t wsel[4];      // dp4a weights: 128 in the byte lane visited k-th
+};
+
+// bytes outside the line become 0x80: their bumps land in the spare row 128 of the chunk (never read back),
+// at the lane's usual bank -- no per-bump guard, no select
+__device__ __forceinline__ uint32_t mask_to_trash(uint32_t v, uint32_t m)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(r) : "r"(v), "r"(m), "r"(0x80808080u));   // (v & m) | (~m & K)
+    return r;
+}
+// 0xFF in the low `n` bytes (n clamped to 0..4)
+__device__ __forceinline__ uint32_t low_bytes_mask(int n)
+{
+    const uint32_t l = (uint32_t)max(min(n, 4), 0);
+    uint32_t m;
+    asm("shr.b32 %0, %1, %2;" : "=r"(m) : "r"(0xFFFFFFFFu), "r"(32u - 8u * l));          // shift amounts >= 32 give 0
+    return m;
+}
+
+template <class C, int S>
+struct LSteps {
+    static __device__ __forceinline__ void run(uint32_t a0, uint32_t sh, int left0, uint32_t nmax, uint32_t nmin,
+                                               const StepK& sk, uint32_t& hib)
+    {
+        if (64u * S >= nmax) return;                                      // warp-uniform
+        const uint32_t w0 = lds32<64 * S>(a0), w1 = lds32<64 * S + 4>(a0);
+        uint32_t v = __funnelshift_r(w0, w1, sh);
+        constexpr int CO = 4 * C::CHUNK_WORDS * 2 * S;                    // byte offset of chunk 2 S
+        if (64u * (S + 1) <= nmin) {                                      // every lane's word lies inside its line
+            hib |= v;
+        } else {
+            const uint32_t m = low_bytes_mask(left0 - 64 * S);           // bytes of the line in this lane's word
+            hib |= v & m;
+            v = mask_to_trash(v, m);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red_add<CO>(dp4a_u(v, sk.wsel[k], sk.hk[k]), sk.inc);
+        LSteps<C, S + 1>::run(a0, sh, left0, nmax, nmin, sk, hib);
+    }
+};
+template <class C>
+struct LSteps<C, (C::PPAD + 63) / 64> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, int, uint32_t, uint32_t, const StepK&, uint32_t&) {}
+};
+
+// ps / pq: (window offset of the line) | (bytes of it with a counter) << 16, of ONE record, warp-uniform
+template <class C>
+__device__ __forceinline__ void line_steps(uint32_t ps, uint32_t pq, bool qhalf, const StepK& sk, uint32_t& hib)
+{
+    const uint32_t ns = ps >> 16, nq = pq >> 16;
+    const uint32_t pk = qhalf ? pq : ps;
+    const uint32_t addr = sk.lane_base + (pk & 0xFFFFu);                  // shared address of this lane's word in step 0
+    LSteps<C, 0>::run(addr & ~3u, addr << 3, (int)(pk >> 16) - (int)sk.lane_pos, max(ns, nq), min(ns, nq), sk, hib);
+}
+
+struct RecSink {   // where validate_block accounts the records of a scanned window
+    unsigned long long* stats;
+    unsigned long long* seqraw;
+    uint32_t* lenh;
+    uint32_t max_len;
+};
+
+template <class C, bool HIST>
+__device__ __forceinline__ uint32_t validate_block(const RecSink& p, const uint8_t* buf, uint32_t buf_s, uint32_t Pm,
+                                                   uint32_t n_rec, uint32_t base, int lane, uint32_t& ps, uint32_t& pq,
+                                                   WinAcc& wa)
+{
+    uint32_t* const lenh = p.lenh;
+    const uint32_t r = base + (uint32_t)lane;
+    const bool valid = r < n_rec;
+    // lanes without a record look at record 0 of the window (real data, harmless) and are masked out below
+    const uint32_t lp = buf_s + (uint32_t)(C::WIN + 16) + (valid ? 8u * r : 0u);
+    // (the bound keeps every address derived from the list inside this warp's buffer even if a byte >= 0x80
+    // in another warp's sequence line made a bump of that warp land in this list -- the launch is void then)
+    constexpr uint32_t LIM = (uint32_t)C::WIN + 15u;
+    const uint32_t s = min(lds_u16<0>(lp), LIM), h = min(lds_u16<2>(lp) - 1u, LIM), q = min(lds_u16<4>(lp) - 1u, LIM),
+                   pp = min(lds_u16<6>(lp) - 1u, LIM), e = min(lds_u16<8>(lp) - 1u, LIM);
+    const uint32_t c_at = lds_u8(buf_s + s), c_plus = lds_u8(buf_s + q + 1u), c_sr = lds_u8(buf_s + q - 1u),
+                   c_qr = lds_u8(buf_s + e - 1u);
+    // src/records.rs:137-149 ('@'), :151-163 ('+'), :233-238 (raw line lengths equal)
+    const bool good = c_at == '@' && c_plus == '+' && (e - pp) == (q - h);
+    const unsigned nok = __ballot_sync(0xffffffffu, valid && !good);
+    const uint32_t first_bad = nok ? base + (uint32_t)__ffs(nok) - 1u : NO_START;
+    const bool ok = valid && r < first_bad;
+    ps = 0;
+    pq = 0;
+    if (HIST) {
+        if (ok) {
+            const uint32_t P = p.max_len;
+            const uint32_t Lr = q - h - 1u;
+            // seq()/qual() drop one trailing '\r' (src/records.rs:65-73,82-90)
+            const uint32_t Ls = Lr - ((Lr > 0 && c_sr == '\r') ? 1u : 0u);
+            const uint32_t Lq = Lr - ((Lr > 0 && c_qr == '\r') ? 1u : 0u);
+            wa.n_records++;
+            wa.n_bases += Ls;
+            if (max(Ls, Lq) > P) {                                        // longer than the tracked positions: rare
+                if (Ls > P) atomicAdd(p.stats + 2, (unsigned long long)(Ls - P));
+                if (Lq > P) atomicAdd(p.stats + 3, (unsigned long long)(Lq - P));
+            }
+            const uint32_t lb = Ls <= P ? Ls : P + 1u;
+            if (lb < (uint32_t)C::PPAD + 2u)
+                atomicAdd(lenh + lb, 1u);
+            else
+                atomicAdd(p.stats + stats_len_off(P) + lb, 1ull);
+            ps = (h + 1u) | (min(Ls, Pm) << 16);
+            pq = (pp + 1u) | (min(Lq, Pm) << 16);
+            // positions beyond the shared-memory columns but below P: straight to global (P > PPAD only)
+            if (P > Pm) {
+                const uint32_t gs = min(Ls, P), gq = min(Lq, P);
+                unsigned long long* gqual = p.stats + stats_qual_off(P);
+                for (uint32_t g = Pm; g < gs; ++g) atomicAdd(p.seqraw + (size_t)g * 256 + buf[h + 1u + g], 1ull);
+                for (uint32_t g = Pm; g < gq; ++g) atomicAdd(gqual + (size_t)g * 256 + buf[pp + 1u + g], 1ull);
+            }
+        }
+    } else if (ok) {
+        wa.n_records++;
+    }
+    return first_bad;
+}
+
+// ------------------------------------------------------------------------------------------
 // PREDICTED windows.  While the records keep the shape of the last record a scan delimited (line
 // lengths Lh, Lsq, Lp, Lsq with their '\n'; '\r' before the '\n' of the sequence / quality line or
 // not), a window is not scanned at all: record r starts at pad + r * reclen and is VERIFIED instead:
@@ -517,13 +656,181 @@ __device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t 
 struct StreamCta {
     uint32_t n_records, n_bases;   // totals of the CTA (u32: a CTA sees < 4 G bases per launch; native shared atomics)
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
-    uint32_t pad;
+    uint32_t flush_epoch;   // bumped by the warp that pushes `recs` over a multiple of DRAIN_MARK
+    uint32_t orphans;       // bit w: warp w is not (or no longer) inside its range loop -- it cannot drain its slice
 };
 constexpr uint32_t DRAIN_MARK = 24000u;   // records a CTA consumes between two drains of its u16 counter halves
 
+// u16 counter halves: the warp that pushes the CTA-wide record count over a multiple of the mark starts a drain
+// epoch.  Every warp still inside its range loop drains ITS slice of the table when it notices (at the end of
+// its current window) -- lock-free: atomicExch leaves the other warps' concurrent bumps intact.  The slices of
+// warps that have left their loop (or never had a range) are ORPHANS: the warp that starts the epoch drains
+// those as well, there and then.  So every counter is drained within one window's time of every epoch,
+// whatever the other warps are doing: between two drains of a counter the CTA consumes DRAIN_MARK records plus
+// the few hundred of one window per warp -- far below 65 535 per half, for any input.
+template <class C>
+__device__ __forceinline__ void drain_tick(uint32_t* hist, const ScanParams& p, StreamCta& cta, uint32_t n_rec,
+                                           uint32_t& my_epoch, int warp, int lane)
+{
+    constexpr int SLICE = (C::HIST_WORDS + C::NWARPS - 1) / C::NWARPS;
+    uint32_t trip = 0;
+    if (lane == 0) {
+        const uint32_t before = atomicAdd(&cta.recs, n_rec);
+        if (before / DRAIN_MARK != (before + n_rec) / DRAIN_MARK) {
+            atomicAdd(&cta.flush_epoch, 1u);
+            trip = 1;
+        }
+    }
+    const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(&cta.flush_epoch);
+    if (ep != my_epoch) {
+        my_epoch = ep;
+        flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
+    }
+    if (__shfl_sync(0xffffffffu, trip, 0)) {
+        uint32_t m = *reinterpret_cast<volatile uint32_t*>(&cta.orphans);
+        while (m) {
+            const int w = __ffs(m) - 1;
+            m &= m - 1u;
+            flush_hist<C>(hist, p, w * SLICE, min((w + 1) * SLICE, C::HIST_WORDS), lane, 32);
+        }
+    }
+}
+// a warp leaves its range loop (or has no range): its slice is an orphan from now on; one last drain of its own
+template <class C>
+__device__ __forceinline__ void drain_leave(uint32_t* hist, const ScanParams& p, StreamCta& cta, int warp, int lane)
+{
+    constexpr int SLICE = (C::HIST_WORDS + C::NWARPS - 1) / C::NWARPS;
+    if (lane == 0) atomicOr(&cta.orphans, 1u << warp);
+    __syncwarp();
+    flush_hist<C>(hist, p, warp * SLICE, min((warp + 1) * SLICE, C::HIST_WORDS), lane, 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// VARIABLE-shape stretch of a range (reads of varying length: nothing to predict).  Every window is scanned;
+// its records are validated 32 at a time, one per lane, and counted one record at a time by the whole warp
+// (validate_block / line_steps).  A separate loop -- not a branch of the loop over predicted windows -- so
+// that neither weighs on the other's registers (the two live in different instantiations of the kernel).
+// ------------------------------------------------------------------------------------------
+struct RangeState {          // what the two loops over a range hand to each other
+    unsigned long long cur;      // cursor: buffer offset of the next record
+    unsigned long long lrank;    // line ends of the range staged so far
+    unsigned long long tail_x;   // offset of the bad / incomplete record that ends an EOF shard (NONE64: none)
+    uint32_t parity;             // phase of the warp's mbarrier
+    uint32_t epoch;              // last drain epoch this warp has served
+    uint32_t dbg_scan;
+    bool failed;
+};
+
+template <class C>
+__device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint32_t buf_s, uint16_t* list,
+                                         unsigned long long* bar, uint32_t* hist, uint32_t* lenh, uint32_t hist_s,
+                                         StreamCta& cta, uint32_t rid, unsigned long long R1, bool last_eof,
+                                         bool want_index, RangeState& rs, int warp, int lane, uint32_t lt_mask)
+{
+    const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
+    const RecSink sink = {p.stats, p.seqraw, lenh, p.max_len};
+    const bool qhalf = lane >= 16;
+    StepK sk;
+    {
+        const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
+        sk.lane_pos = 4u * ((uint32_t)lane & 15u);
+        sk.lane_base = buf_s + sk.lane_pos;
+        sk.inc = qhalf ? 0x10000u : 1u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
+            sk.hk[kk] = hist_s + 4u * (4u * i + bytek) + (sub & 1u) * (uint32_t)(4 * C::CHUNK_WORDS);
+            sk.wsel[kk] = 128u << (8u * bytek);
+            asm volatile("" : "+r"(sk.hk[kk]), "+r"(sk.wsel[kk]));
+        }
+    }
+    while (!rs.failed && rs.cur < R1 && rs.cur < p.n_avail) {
+        const Window w = win_load<C>(p, buf, bar, rs.parity, (long long)rs.cur, lane);
+        const unsigned long long room = R1 - w.src;          // > pad: window bytes inside the range
+        ++rs.dbg_scan;
+        uint32_t hib_unused;
+        const uint32_t total = win_scan<C, false>(buf_s, list, w, hib_unused, lane, lt_mask);
+        const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
+        if (n_win == 0 && last_eof && w.vlen < (uint32_t)C::WIN) {
+            rs.tail_x = rs.cur;   // the stream ends inside this record (or in garbage): the first bad record
+            break;
+        }
+        if (n_win == 0) {
+            rs.failed = true;     // a record longer than the window, data ending inside a record
+            break;
+        }
+        // records of the window that start inside the range (their starts increase)
+        uint32_t n_rec = n_win;
+        if (room < (unsigned long long)C::WIN) {              // the range ends inside this window
+            const uint32_t ra = (uint32_t)lane, rb = (uint32_t)lane + 32u;
+            const bool va = ra < n_win && list[4u * ra] < (uint32_t)room;
+            const bool vb = rb < n_win && list[4u * min(rb, (uint32_t)C::MAXR)] < (uint32_t)room;
+            n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
+        }
+        WinAcc wa = {0, 0};
+        uint32_t first_bad = NO_START, hib = 0;
+        for (uint32_t b0 = 0; b0 < n_rec && first_bad == NO_START; b0 += 32u) {
+            uint32_t ps, pq;
+            first_bad = validate_block<C, true>(sink, buf, buf_s, Pm, n_rec, b0, lane, ps, pq, wa);
+            const uint32_t cnt = min(min(n_rec, first_bad) - b0, 32u);
+            for (uint32_t r = 0; r < cnt; ++r)
+                line_steps<C>(__shfl_sync(0xffffffffu, ps, r), __shfl_sync(0xffffffffu, pq, r), qhalf, sk, hib);
+        }
+        // bytes >= 0x80 in a sequence or quality line (id and separator lines may hold anything): their bumps
+        // left the table rows -- the exact path redoes the shard (see pred_pass)
+        if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+            rs.failed = true;
+            break;
+        }
+        if (first_bad != NO_START) {
+            if (!last_eof) {
+                rs.failed = true;   // a record that fails validation: the exact path finds and classifies it
+                break;
+            }
+            n_rec = first_bad;      // the records in front of it stand; the range ends at the bad one
+            rs.tail_x = (unsigned long long)(w.src + (long long)list[4u * first_bad]);
+        }
+        {
+            const uint32_t nr = __reduce_add_sync(0xffffffffu, wa.n_records), nb = __reduce_add_sync(0xffffffffu, wa.n_bases);
+            if (lane == 0) {
+                atomicAdd(&cta.n_records, nr);
+                atomicAdd(&cta.n_bases, nb);
+            }
+        }
+        // line ends of the consumed records that lie in the owned bytes of the shard
+        uint32_t n_lines = 4u * n_rec;
+        const uint32_t next = list[n_lines];                  // start of the first record not consumed
+        if (next <= w.pad && rs.tail_x == NONE64) {           // (only a list another warp's stray bump damaged)
+            rs.failed = true;
+            break;
+        }
+        if (w.src + next - 1u >= p.n_own) {                   // the shard's last record reaches beyond n_own
+            const bool in = lane < 4 && w.src + list[n_lines - 3u + (uint32_t)lane] - 1u < p.n_own;
+            n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (want_index) {
+            if (rs.lrank + n_lines > p.stage_share) {
+                rs.failed = true;   // staging share too small: the exact path writes the index
+                break;
+            }
+            const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;   // low 32 bits are what the index holds
+            uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + rs.lrank;
+            const uint32_t ls = buf_s + (uint32_t)(C::WIN + 16) + 2u;
+            for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + lds_u16<0>(ls + 2u * j);
+        }
+        rs.lrank += n_lines;
+        rs.cur = w.src + next;
+        if (rs.tail_x != NONE64) break;
+        drain_tick<C>(hist, p, cta, n_rec, rs.epoch, warp, lane);   // u16 counter halves
+    }
+}
+
 // HIST: the launch accumulates the per-position histograms (FQB_F_HIST); the two variants share no
 // hot code (rounds + '\n'-row check vs. newline count), so each is compiled without the other's registers
-template <class C, bool HIST>
+// VAR: the variant for reads of varying length (every window scanned, records counted by line_steps); the
+// other variant predicts.  Both are launched; fq_init_kernel's look at the head of the shard (res->shape_var)
+// decides which of them does the work -- either one is correct on any input, they differ in what they are fast on.
+template <class C, bool HIST, bool VAR>
 __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -538,6 +845,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     if (p.res->spec_fail) return;                              // the host sent this shard to the exact path
+    if ((p.res->shape_var != 0) != VAR) return;                // the other variant's kind of input
     if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
     const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
 
@@ -547,6 +855,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         cta.n_records = 0;
         cta.n_bases = 0;
         cta.recs = 0;
+        cta.flush_epoch = 0;
+        cta.orphans = 0;
     }
     fence_mbar_init();
     __syncthreads();
@@ -583,6 +893,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
 
     unsigned long long cur = 0, lrank = 0;
     bool failed = false;
+    uint32_t my_epoch = 0;
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
@@ -592,7 +903,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             const bool front = rid != 0 || (p.flags & F_FRONT16);
             const Window w = win_load<C>(p, buf, bar, parity, (long long)R0 - (front ? 1 : 0), lane);
             uint32_t hib;
-            const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
+            const uint32_t total = win_scan<C, HIST && !VAR>(buf_s, list, w, hib, lane, lt_mask);
             const uint32_t nstored = min(total, (uint32_t)C::LIST_DUMMY - 1u);
             const uint32_t neg = (front && nstored >= 1u && list[1] == 16u) ? 1u : 0u;   // a '\n' right in front of the range
             uint32_t c;
@@ -605,8 +916,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t K = (line_start && phase == 0) ? 0u : 4u - phase;
                 c = K + neg <= nstored ? K + neg : NO_START;
             }
-            // (bytes >= 0x80 only matter to the histogram addressing: without histograms any byte will do)
-            if (c == NO_START || (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
+            // (bytes >= 0x80 only matter to the histogram addressing: without histograms any byte will do; the
+            // variable-length variant checks the sequence and quality lines themselves, see line_steps)
+            if (c == NO_START || (HIST && !VAR && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
                 failed = true;
             } else {
                 cur = (unsigned long long)(w.src + (long long)list[c]);
@@ -645,7 +957,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
-        while (!failed && cur < R1 && cur < p.n_avail) {
+        if (VAR) {
+            // ---- reads of varying length: every window is scanned (var_loop) ---------------------------
+            RangeState rs = {cur, lrank, tail_x, parity, my_epoch, dbg_scan, failed};
+            var_loop<C>(p, buf, buf_s, list, bar, hist, lenh, hist_s, cta, rid, R1, last_eof, want_index, rs, warp, lane,
+                        lt_mask);
+            cur = rs.cur;
+            lrank = rs.lrank;
+            tail_x = rs.tail_x;
+            dbg_scan = rs.dbg_scan;
+            failed = rs.failed;
+        }
+        while (!VAR && !failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
             const unsigned long long room = R1 - w.src;          // > pad: window bytes inside the range
             uint32_t n_rec, n_lines, next;
@@ -811,7 +1134,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 // ---- scanned window -------------------------------------------------------------------
                 ++dbg_scan;
                 uint32_t hib;
-                const uint32_t total = win_scan<C>(buf_s, list, w, hib, lane, lt_mask);
+                const uint32_t total = win_scan<C, HIST>(buf_s, list, w, hib, lane, lt_mask);
                 const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
                 if (n_win == 0 && last_eof && w.vlen < (uint32_t)C::WIN &&
                     !(HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
@@ -927,20 +1250,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             lrank += n_lines;
             cur = w.src + next;
             if (tail_x != NONE64) break;
-            // u16 counter halves: the warp that pushes the CTA-wide record count over a multiple of the mark
-            // drains the WHOLE table, there and then (lock-free: atomicExch leaves the other warps' concurrent
-            // bumps intact).  The drain does not depend on any other warp still being inside its range loop --
-            // warps that have finished (or never were live) take no part in it -- so between two drains of a
-            // counter the CTA consumes at most DRAIN_MARK records plus the few thousand it gets through while
-            // one warp walks the table (~20 K words): far below 65 535 per half, whatever the input looks like.
-            if (HIST) {
-                uint32_t trip = 0;
-                if (lane == 0) {
-                    const uint32_t before = atomicAdd(&cta.recs, n_rec);
-                    trip = before / DRAIN_MARK != (before + n_rec) / DRAIN_MARK ? 1u : 0u;
-                }
-                if (__shfl_sync(0xffffffffu, trip, 0)) flush_hist<C>(hist, p, 0, C::HIST_WORDS, lane, 32);
-            }
+            if (HIST) drain_tick<C>(hist, p, cta, n_rec, my_epoch, warp, lane);   // u16 counter halves
         }
         if (tail_x != NONE64 && !failed) {
             // (the line ends of the bytes behind it are counted and indexed by fq_tail_index_kernel)
@@ -964,6 +1274,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     }
 
     // ---- drain -----------------------------------------------------------------------------
+    if (HIST) drain_leave<C>(hist, p, cta, warp, lane);       // (warps still at work drain this warp's slice from now on)
     __syncthreads();
     flush_hist<C>(hist, p, 0, C::HIST_WORDS, tid, C::NTHREADS);
     {
@@ -1068,38 +1379,48 @@ using SCfg5 = SCfg<5, 32, 4096>;     // P <= 160: 80 KB of counters, 32 warps x 
 using SCfg10 = SCfg<10, 22, 2560>;   // P <= 320: 160 KB of counters, 22 warps x 2.5 KiB windows (measured best of
                                      // 16 x 3584 / 22 x 2560 / 26 x 2048 on fixed 300 bp and on 50..300 bp reads)
 
+// the variable-length variants: same ranges (the host cuts the shard into grid x NWARPS of them), a spare row per chunk
+using VCfg5 = SCfg<5, 32, 4096, 1>;
+using VCfg10 = SCfg<10, 22, 2560, 1>;
+static_assert(VCfg5::NWARPS == SCfg5::NWARPS && VCfg10::NWARPS == SCfg10::NWARPS, "both variants walk the same ranges");
+
 int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }
 
-template <class C>
-static cudaError_t configure_pair()
+template <class C, class V>
+static cudaError_t configure_set()
 {
-    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fq_stream_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
+    e = cudaFuncSetAttribute(fq_stream_kernel<V, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V::TOTAL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fq_stream_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
 }
 
 cudaError_t stream_configure()
 {
-    cudaError_t e = configure_pair<SCfg5>();
+    cudaError_t e = configure_set<SCfg5, VCfg5>();
     if (e != cudaSuccess) return e;
-    return configure_pair<SCfg10>();
+    return configure_set<SCfg10, VCfg10>();
 }
 
-template <class C>
-static void launch_pair(const ScanParams& p, int grid, cudaStream_t st)
+template <class C, class V>
+static void launch_set(const ScanParams& p, int grid, cudaStream_t st)
 {
-    if (p.flags & F_HIST)
-        fq_stream_kernel<C, true><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
-    else
-        fq_stream_kernel<C, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+    if (p.flags & F_HIST) {
+        // (one of the two returns at once: res->shape_var, set by fq_init_kernel's look at the head of the shard)
+        fq_stream_kernel<C, true, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+        fq_stream_kernel<V, true, true><<<grid, V::NTHREADS, V::TOTAL, st>>>(p);
+    } else {
+        fq_stream_kernel<C, false, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+    }
 }
 
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st)
 {
     if (nchunk <= 5)
-        launch_pair<SCfg5>(p, grid, st);
+        launch_set<SCfg5, VCfg5>(p, grid, st);
     else
-        launch_pair<SCfg10>(p, grid, st);
+        launch_set<SCfg10, VCfg10>(p, grid, st);
     return cudaGetLastError();
 }
 
