@@ -80,7 +80,7 @@ __device__ void flush_hist(uint32_t* hist, const ScanParams& p, int first, int l
     for (int i = first + tid; i < last; i += nthreads) {
         if (hist[i] == 0) continue;
         const uint32_t chunk = (uint32_t)i / C::CHUNK_WORDS, r = (uint32_t)i % C::CHUNK_WORDS;
-        const uint32_t b = r >> 5, pos = chunk * 32u + (r & 31u);
+        const uint32_t b = (r >> 5) + (uint32_t)C::ROW0, pos = chunk * 32u + (r & 31u);   // (first row = byte ROW0)
         if (b >= (uint32_t)HIST_ROWS) continue;      // spare row of the speculative kernel's table: never read back
         const uint32_t v = atomicExch(hist + i, 0u);
         const uint32_t lo = v & 0xFFFFu, hi = v >> 16;

@@ -44,6 +44,7 @@ struct Cfg {
     static constexpr int LIST_DUMMY = LIST_CAP + 16;       // writes beyond the capacity land here
     static constexpr int LIST_BYTES = (LIST_CAP * 2 + 64 + 127) / 128 * 128;
     static constexpr int CHUNK_WORDS = HIST_ROWS * 32;     // one 32-position chunk: [byte][32] u32
+    static constexpr int ROW0 = 0;                         // (first byte value with a row: all of them)
     static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;   // u32 = lo16 seq | hi16 qual
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
     // word loads of the record pass may run up to PPAD + 8 bytes past a tile buffer: keep them inside

@@ -35,16 +35,23 @@
 
 namespace fq {
 
-template <int NCHUNK_, int NWARPS_, int WIN_, int SPARE_ROW_ = 0>
+template <int NCHUNK_, int NWARPS_, int WIN_, int SPARE_ROW_ = 0, int ROW0_ = 0>
 struct SCfg {
     static constexpr int NCHUNK = NCHUNK_;
     static constexpr int NWARPS = NWARPS_;                 // autonomous warps per CTA
     static constexpr int NTHREADS = 32 * NWARPS_;
     static constexpr int PPAD = 32 * NCHUNK;
-    // 128 byte rows (+ a spare row in the variable-length variant, see mask_to_trash)
-    static constexpr int CHUNK_WORDS = (HIST_ROWS + SPARE_ROW_) * 32;
+    // byte rows ROW0 .. 127 (+ a spare row in the variable-length variant, see mask_to_trash).  ROW0 = 32 leaves
+    // out the control characters: 25 % less table, which buys the P <= 320 variant 4 KiB windows.  A byte
+    // below ROW0 inside a sequence or quality line is noticed (line_steps) and sends the shard to the exact
+    // path; its bump lands ROW0 rows below its chunk -- in the previous chunk, or in the PRE bytes in front
+    // of the table (which is where the length histogram lives then): never outside the CTA's shared memory.
+    static constexpr int ROW0 = ROW0_;
+    static constexpr int ROWS = HIST_ROWS - ROW0_;             // rows read back (the spare row follows them)
+    static constexpr int CHUNK_WORDS = (ROWS + SPARE_ROW_) * 32;
     static constexpr int HIST_WORDS = NCHUNK * CHUNK_WORDS;
     static constexpr int LENH_WORDS = (PPAD + 2 + 31) / 32 * 32;
+    static constexpr int PRE = ROW0_ ? (ROW0_ * 128 > LENH_WORDS * 4 ? ROW0_ * 128 : LENH_WORDS * 4) : 0;
     static constexpr int WIN = WIN_;                       // window bytes (a multiple of 512)
     static constexpr int NU = WIN / UNIT;                  // 512-byte units per window
     static constexpr int LIST_N = WIN_ >= 4096 ? 192 : 128;   // u16 entries: [0] = cursor, [j] = start of the line after the j-th '\n'
@@ -52,7 +59,8 @@ struct SCfg {
     static constexpr int LIST_DUMMY = LIST_N - 1;          // writes beyond the capacity land here
     static constexpr int WARP_BYTES = WIN + 16 + LIST_N * 2;
     static constexpr int TAIL_PAD = 256;                   // word loads of the rounds may run past the last buffer
-    static constexpr int TOTAL = HIST_WORDS * 4 + LENH_WORDS * 4 + NWARPS * WARP_BYTES + TAIL_PAD;
+    static constexpr int BUF0 = PRE + HIST_WORDS * 4 + (ROW0_ ? 0 : LENH_WORDS * 4);   // offset of the warp buffers
+    static constexpr int TOTAL = BUF0 + NWARPS * WARP_BYTES + TAIL_PAD;
     static_assert(WIN % UNIT == 0 && WIN <= 65520, "window");
     static_assert(TOTAL <= 232448 - 1024, "shared memory per CTA");
     static_assert(WARP_BYTES % 16 == 0, "TMA destination alignment");
@@ -140,11 +148,44 @@ __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, un
 
 // One pass over the window: newline masks, ranks and the list of line starts
 //   list[0] = cursor, list[j] = position after the j-th '\n' of [pad, vlen)
-// The ranks need no second pass: the running count is warp-local.  Per 512-byte unit the per-lane
+// The ranks need no second pass: the running count is warp-local.  Per unit (one piece per lane) the per-lane
 // counts (0, 1, rarely 2) are prefix-summed with two ballots; a piece with three or more newlines
 // sends the unit through the generic path.  Returns the newline count; HIB: hib = OR of all words.
 // RAGGED: the window is shorter than WIN (the end of the shard) -- stale bytes are masked out.
-template <class C, bool RAGGED, bool HIB>
+
+// ranks + list entries of one unit: bit b of this lane's mask mm = a '\n' whose list entry is pos1 + b
+template <class C>
+__device__ __forceinline__ void scan_rank_store(uint32_t mm, uint32_t pos1, uint32_t& ubase, uint32_t list_s,
+                                                uint16_t* list, uint32_t lt_mask)
+{
+    const int c = __popc(mm);
+    const unsigned b1 = __ballot_sync(0xffffffffu, mm != 0);
+    const unsigned b2 = __ballot_sync(0xffffffffu, c > 1);
+    const unsigned b3 = __ballot_sync(0xffffffffu, c > 2);
+    if (!b3) {
+        const uint32_t rank = min(ubase + (uint32_t)__popc(b1 & lt_mask) + (uint32_t)__popc(b2 & lt_mask),
+                                  (uint32_t)C::LIST_DUMMY - 1u);
+        const uint32_t a = list_s + 2u * rank;
+        // the first and the last newline of the piece: lowest and highest set bit
+        if (mm != 0) sts16(a, pos1 + (uint32_t)__clz(__brev(mm)));
+        if (c > 1) sts16(a + 2u, pos1 + 31u - (uint32_t)__clz(mm));
+        ubase += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
+    } else {
+        uint32_t rank = ubase + small_prefix(c, lt_mask);
+        while (mm) {
+            list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(mm) - 1u);
+            mm &= mm - 1u;
+            ++rank;
+        }
+        ubase += __reduce_add_sync(0xffffffffu, (uint32_t)c);
+    }
+}
+
+// WIDE: units of 1 KiB, 32 contiguous bytes per lane (two 16-byte loads -- lanes 4..7 of every 8 take their
+// second piece first, so that each quarter warp's LDS.128 touches all 32 banks once), one set of ballots,
+// ranks and list stores per 32 bytes instead of per 16; what is left of the window (WIN % 1024) goes in
+// 512-byte units.  The variable-length variant scans every window: this is ~1/3 off its scan.
+template <class C, bool RAGGED, bool HIB, bool WIDE>
 __device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib, int lane,
                                                uint32_t lt_mask)
 {
@@ -153,52 +194,50 @@ __device__ __forceinline__ uint32_t win_scan_t(uint32_t buf_s, uint16_t* list, c
     if (lane == 0) sts16(list_s, w.pad);
     uint32_t ubase = 1;
     hib = 0;
-    const uint32_t lane_pos = (uint32_t)lane * 16u - 7u + 1u;              // bit index -> position + 1
+    constexpr int NW = WIDE ? C::WIN / 1024 : 0;                           // 1 KiB units
+    constexpr int N16 = (C::WIN - 1024 * NW) / UNIT;                       // 512-byte units behind them
+    if (WIDE) {
+        const uint32_t odd = ((uint32_t)lane >> 2) & 1u;
 #pragma unroll
-    for (int it = 0; it < C::NU; ++it) {
-        const uint32_t off = (uint32_t)it * UNIT + (uint32_t)lane * 16u;
+        for (int it = 0; it < NW; ++it) {
+            const uint32_t off = (uint32_t)it * 1024u + (uint32_t)lane * 32u;
+            const uint4 va = lds_v4(buf_s + off + 16u * odd);
+            const uint4 vb = lds_v4(buf_s + off + 16u * (odd ^ 1u));
+            if (HIB) hib |= va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w;
+            const uint32_t ma = nlmask16k(va, kA, kB), mb = nlmask16k(vb, kA, kB);   // bit 7 + i = byte i of the piece
+            uint32_t mm = ((odd ? mb : ma) >> 7) | ((odd ? ma : mb) << 9);           // bit i = byte i of the 32 bytes
+            if (it == 0 && lane == 0) mm &= ~((1u << w.pad) - 1u);                   // bytes before the cursor
+            if (RAGGED) {                                                            // stale bytes beyond the data
+                const int rem = (int)w.vlen - (int)off;
+                mm &= rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+            }
+            scan_rank_store<C>(mm, off + 1u, ubase, list_s, list, lt_mask);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < N16; ++it) {
+        const uint32_t off = (uint32_t)(1024 * NW + it * UNIT) + (uint32_t)lane * 16u;
         const uint4 v = lds_v4(buf_s + off);
         if (HIB) hib |= v.x | v.y | v.z | v.w;
         uint32_t mm = nlmask16k(v, kA, kB);                                 // bit 7 + i = byte i of the piece
-        if (it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
+        if (NW == 0 && it == 0 && lane == 0) mm &= ~(((1u << w.pad) - 1u) << 7);      // bytes before the cursor
         if (RAGGED) {                                                       // stale bytes beyond the data
             const int rem = (int)w.vlen - (int)off;
             const uint32_t m = rem >= 16 ? 0xFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
             mm &= m << 7;
         }
-        const int c = __popc(mm);
-        const unsigned b1 = __ballot_sync(0xffffffffu, mm != 0);
-        const unsigned b2 = __ballot_sync(0xffffffffu, c > 1);
-        const unsigned b3 = __ballot_sync(0xffffffffu, c > 2);
-        const uint32_t pos1 = (uint32_t)it * UNIT + lane_pos;
-        if (!b3) {
-            const uint32_t rank = min(ubase + (uint32_t)__popc(b1 & lt_mask) + (uint32_t)__popc(b2 & lt_mask),
-                                      (uint32_t)C::LIST_DUMMY - 1u);
-            const uint32_t a = list_s + 2u * rank;
-            // the first and the last newline of the piece: lowest and highest set bit
-            if (mm != 0) sts16(a, pos1 + (uint32_t)__clz(__brev(mm)));
-            if (c > 1) sts16(a + 2u, pos1 + 31u - (uint32_t)__clz(mm));
-            ubase += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
-        } else {
-            uint32_t rank = ubase + small_prefix(c, lt_mask);
-            while (mm) {
-                list[min(rank, (uint32_t)C::LIST_DUMMY)] = (uint16_t)(pos1 + (uint32_t)__ffs(mm) - 1u);
-                mm &= mm - 1u;
-                ++rank;
-            }
-            ubase += __reduce_add_sync(0xffffffffu, (uint32_t)c);
-        }
+        scan_rank_store<C>(mm, off - 7u + 1u, ubase, list_s, list, lt_mask);
     }
     __syncwarp();
     return ubase - 1u;
 }
 
-template <class C, bool HIB>
+template <class C, bool HIB, bool WIDE = false>
 __device__ __forceinline__ uint32_t win_scan(uint32_t buf_s, uint16_t* list, const Window& w, uint32_t& hib, int lane,
                                              uint32_t lt_mask)
 {
-    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true, HIB>(buf_s, list, w, hib, lane, lt_mask);
-    return win_scan_t<C, false, HIB>(buf_s, list, w, hib, lane, lt_mask);
+    if (w.vlen < (uint32_t)C::WIN) return win_scan_t<C, true, HIB, WIDE>(buf_s, list, w, hib, lane, lt_mask);
+    return win_scan_t<C, false, HIB, WIDE>(buf_s, list, w, hib, lane, lt_mask);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -426,6 +465,7 @@ struct StepK {    // per-lane constants of line_steps (made once per stretch of 
     uint32_t lane_base;    // buf_s + 4 * (lane & 15)
     uint32_t lane_pos;     // 4 * (lane & 15): position of this lane's word in step 0
     uint32_t inc;          // 1 for the sequence half, 0x10000 for the quality half
+    uint32_t gofs;         // byte offset of the chunk of the lane's word within a step (0 or one chunk)
     uint32_t hk[4];        // shared address of hist[chunk of the lane's word in step 0][0][position visited k-th]
     uint32_t wsel[4];      // dp4a weights: 128 in the byte lane visited k-th
 };
@@ -447,40 +487,98 @@ __device__ __forceinline__ uint32_t low_bytes_mask(int n)
     return m;
 }
 
+// one step in which every lane's word lies inside its line: no guard (S: compile-time step number)
+// (lob: AND of (byte | byte << 1) over the bytes counted: bit 6 stays set iff all of them are >= 32 -- only
+// kept when the table leaves out the rows below ROW0 = 32)
 template <class C, int S>
-struct LSteps {
-    static __device__ __forceinline__ void run(uint32_t a0, uint32_t sh, int left0, uint32_t nmax, uint32_t nmin,
-                                               const StepK& sk, uint32_t& hib)
-    {
-        if (64u * S >= nmax) return;                                      // warp-uniform
-        const uint32_t w0 = lds32<64 * S>(a0), w1 = lds32<64 * S + 4>(a0);
-        uint32_t v = __funnelshift_r(w0, w1, sh);
-        constexpr int CO = 4 * C::CHUNK_WORDS * 2 * S;                    // byte offset of chunk 2 S
-        if (64u * (S + 1) <= nmin) {                                      // every lane's word lies inside its line
-            hib |= v;
-        } else {
-            const uint32_t m = low_bytes_mask(left0 - 64 * S);           // bytes of the line in this lane's word
-            hib |= v & m;
-            v = mask_to_trash(v, m);
-        }
+__device__ __forceinline__ void full_step(uint32_t a0, uint32_t sh, const StepK& sk, uint32_t& hib, uint32_t& lob)
+{
+    const uint32_t w0 = lds32<64 * S>(a0), w1 = lds32<64 * S + 4>(a0);
+    const uint32_t v = __funnelshift_r(w0, w1, sh);
+    constexpr int CO = 4 * C::CHUNK_WORDS * 2 * S;                        // byte offset of chunk 2 S
+    hib |= v;
+    if (C::ROW0) lob &= v | (v << 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red_add<CO>(dp4a_u(v, sk.wsel[k], sk.hk[k]), sk.inc);
+}
+// the step in which the lines end: bytes beyond the line go to the spare row (left0: bytes of the line from
+// this lane's word of step 0 on)
+template <class C, int S>
+__device__ __forceinline__ void last_step(uint32_t a0, uint32_t sh, int left0, const StepK& sk, uint32_t& hib,
+                                          uint32_t& lob)
+{
+    const uint32_t w0 = lds32<64 * S>(a0), w1 = lds32<64 * S + 4>(a0);
+    uint32_t v = __funnelshift_r(w0, w1, sh);
+    const uint32_t m = low_bytes_mask(left0 - 64 * S);                    // bytes of the line in this lane's word
+    hib |= v & m;
+    if (C::ROW0) lob &= v | (v << 1) | ~m;
+    v = mask_to_trash(v, m);
+    // a lane beyond the last chunk of the table (PPAD % 64 != 0: it never has a byte of the line) bumps the spare
+    // row of the last chunk instead
+    constexpr int CO = 4 * C::CHUNK_WORDS * 2 * S;
+    if (2 * S + 1 < C::NCHUNK) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) red_add<CO>(dp4a_u(v, sk.wsel[k], sk.hk[k]), sk.inc);
-        LSteps<C, S + 1>::run(a0, sh, left0, nmax, nmin, sk, hib);
+    } else {
+        constexpr int CLAST = 4 * C::CHUNK_WORDS * (C::NCHUNK - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red_add<CLAST>(dp4a_u(v, sk.wsel[k], sk.hk[k] - sk.gofs), sk.inc);
     }
-};
+}
+// (S known only at run time: the rare second step of a record whose two lines end in different steps)
 template <class C>
-struct LSteps<C, (C::PPAD + 63) / 64> {
-    static __device__ __forceinline__ void run(uint32_t, uint32_t, int, uint32_t, uint32_t, const StepK&, uint32_t&) {}
-};
+__device__ __noinline__ void last_step_any(uint32_t S, uint32_t a0, uint32_t sh, int left0, uint32_t hk0, uint32_t hk1,
+                                           uint32_t hk2, uint32_t hk3, uint32_t w0k, uint32_t w1k, uint32_t w2k,
+                                           uint32_t w3k, uint32_t gofs, uint32_t inc, uint32_t* hib, uint32_t* lob)
+{
+    const uint32_t ao = a0 + 64u * S;
+    uint32_t v = __funnelshift_r(lds32<0>(ao), lds32<4>(ao), sh);
+    const uint32_t m = low_bytes_mask(left0 - 64 * (int)S);
+    *hib |= v & m;
+    if (C::ROW0) *lob &= v | (v << 1) | ~m;
+    v = mask_to_trash(v, m);
+    const uint32_t adj = min(2u * S * (uint32_t)(4 * C::CHUNK_WORDS) + gofs, (uint32_t)((C::NCHUNK - 1) * 4 * C::CHUNK_WORDS)) - gofs;
+    red_add<0>(dp4a_u(v, w0k, hk0 + adj), inc);
+    red_add<0>(dp4a_u(v, w1k, hk1 + adj), inc);
+    red_add<0>(dp4a_u(v, w2k, hk2 + adj), inc);
+    red_add<0>(dp4a_u(v, w3k, hk3 + adj), inc);
+}
 
 // ps / pq: (window offset of the line) | (bytes of it with a counter) << 16, of ONE record, warp-uniform
 template <class C>
-__device__ __forceinline__ void line_steps(uint32_t ps, uint32_t pq, bool qhalf, const StepK& sk, uint32_t& hib)
+__device__ __forceinline__ void line_steps(uint32_t ps, uint32_t pq, bool qhalf, const StepK& sk, uint32_t& hib,
+                                           uint32_t& lob)
 {
+    constexpr int NSTEP = (C::PPAD + 63) / 64;
+    static_assert(NSTEP <= 6, "line_steps: at most 6 steps of 64 positions");
     const uint32_t ns = ps >> 16, nq = pq >> 16;
     const uint32_t pk = qhalf ? pq : ps;
     const uint32_t addr = sk.lane_base + (pk & 0xFFFFu);                  // shared address of this lane's word in step 0
-    LSteps<C, 0>::run(addr & ~3u, addr << 3, (int)(pk >> 16) - (int)sk.lane_pos, max(ns, nq), min(ns, nq), sk, hib);
+    const uint32_t a0 = addr & ~3u, sh = addr << 3;
+    const int left0 = (int)(pk >> 16) - (int)sk.lane_pos;
+    const uint32_t nmax = max(ns, nq);
+    // steps 0 .. nfull - 1 lie inside both lines; the lines end in step nfull (nothing of them is left there when
+    // the length is a multiple of 64: that step then only feeds the spare row).  One computed jump per record:
+    // case k = the guarded step k, then the unguarded steps k - 1 .. 0 as straight-line code.
+    const uint32_t nfull = min(min(ns, nq) >> 6, (uint32_t)(NSTEP - 1));  // (warp-uniform)
+    switch (nfull) {
+    case 5: if (NSTEP > 5) { last_step<C, 5>(a0, sh, left0, sk, hib, lob); goto f4; }
+    case 4: if (NSTEP > 4) { last_step<C, 4>(a0, sh, left0, sk, hib, lob); goto f3; }
+    case 3: if (NSTEP > 3) { last_step<C, 3>(a0, sh, left0, sk, hib, lob); goto f2; }
+    case 2: if (NSTEP > 2) { last_step<C, 2>(a0, sh, left0, sk, hib, lob); goto f1; }
+    case 1: if (NSTEP > 1) { last_step<C, 1>(a0, sh, left0, sk, hib, lob); goto f0; }
+    default: last_step<C, 0>(a0, sh, left0, sk, hib, lob); goto done;
+    }
+f4: if (NSTEP > 5) full_step<C, 4>(a0, sh, sk, hib, lob);
+f3: if (NSTEP > 4) full_step<C, 3>(a0, sh, sk, hib, lob);
+f2: if (NSTEP > 3) full_step<C, 2>(a0, sh, sk, hib, lob);
+f1: if (NSTEP > 2) full_step<C, 1>(a0, sh, sk, hib, lob);
+f0: if (NSTEP > 1) full_step<C, 0>(a0, sh, sk, hib, lob);
+done:
+    // seq() and qual() end in different steps ('\r' trimmed from one of them only, at a multiple of 64): rare
+    if (nmax > 64u * (nfull + 1u))
+        last_step_any<C>(nfull + 1u, a0, sh, left0, sk.hk[0], sk.hk[1], sk.hk[2], sk.hk[3], sk.wsel[0], sk.wsel[1], sk.wsel[2],
+                         sk.wsel[3], sk.gofs, sk.inc, &hib, &lob);
 }
 
 struct RecSink {   // where validate_block accounts the records of a scanned window
@@ -736,20 +834,23 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
         sk.lane_pos = 4u * ((uint32_t)lane & 15u);
         sk.lane_base = buf_s + sk.lane_pos;
         sk.inc = qhalf ? 0x10000u : 1u;
+        sk.gofs = (sub & 1u) * (uint32_t)(4 * C::CHUNK_WORDS);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const uint32_t bytek = ((uint32_t)kk + sub) & 3u;
-            sk.hk[kk] = hist_s + 4u * (4u * i + bytek) + (sub & 1u) * (uint32_t)(4 * C::CHUNK_WORDS);
+            sk.hk[kk] = hist_s - (uint32_t)(C::ROW0 * 128) + 4u * (4u * i + bytek) + sk.gofs;   // (row of byte b: b - ROW0)
             sk.wsel[kk] = 128u << (8u * bytek);
             asm volatile("" : "+r"(sk.hk[kk]), "+r"(sk.wsel[kk]));
         }
+        // (kept in registers: recomputing them for every record costs more than it saves)
+        asm volatile("" : "+r"(sk.lane_pos), "+r"(sk.lane_base), "+r"(sk.inc), "+r"(sk.gofs));
     }
     while (!rs.failed && rs.cur < R1 && rs.cur < p.n_avail) {
         const Window w = win_load<C>(p, buf, bar, rs.parity, (long long)rs.cur, lane);
         const unsigned long long room = R1 - w.src;          // > pad: window bytes inside the range
         ++rs.dbg_scan;
         uint32_t hib_unused;
-        const uint32_t total = win_scan<C, false>(buf_s, list, w, hib_unused, lane, lt_mask);
+        const uint32_t total = win_scan<C, false, true>(buf_s, list, w, hib_unused, lane, lt_mask);
         const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
         if (n_win == 0 && last_eof && w.vlen < (uint32_t)C::WIN) {
             rs.tail_x = rs.cur;   // the stream ends inside this record (or in garbage): the first bad record
@@ -768,16 +869,17 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
             n_rec = (uint32_t)__popc(__ballot_sync(0xffffffffu, va)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, vb));
         }
         WinAcc wa = {0, 0};
-        uint32_t first_bad = NO_START, hib = 0;
+        uint32_t first_bad = NO_START, hib = 0, lob = 0xFFFFFFFFu;
         for (uint32_t b0 = 0; b0 < n_rec && first_bad == NO_START; b0 += 32u) {
             uint32_t ps, pq;
             first_bad = validate_block<C, true>(sink, buf, buf_s, Pm, n_rec, b0, lane, ps, pq, wa);
             const uint32_t cnt = min(min(n_rec, first_bad) - b0, 32u);
             for (uint32_t r = 0; r < cnt; ++r)
-                line_steps<C>(__shfl_sync(0xffffffffu, ps, r), __shfl_sync(0xffffffffu, pq, r), qhalf, sk, hib);
+                line_steps<C>(__shfl_sync(0xffffffffu, ps, r), __shfl_sync(0xffffffffu, pq, r), qhalf, sk, hib, lob);
         }
-        // bytes >= 0x80 in a sequence or quality line (id and separator lines may hold anything): their bumps
-        // left the table rows -- the exact path redoes the shard (see pred_pass)
+        // bytes >= 0x80 (or below the first row of the table) in a sequence or quality line -- id and separator
+        // lines may hold anything --: their bumps left the table rows, the exact path redoes the shard
+        if (C::ROW0) hib |= ~lob << 1;                         // bit 7 of a byte lane: some byte there was < 32
         if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
             rs.failed = true;
             break;
@@ -834,8 +936,8 @@ template <class C, bool HIST, bool VAR>
 __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_constant__ ScanParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* lenh = hist + C::HIST_WORDS;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + C::PRE);
+    uint32_t* lenh = C::ROW0 ? reinterpret_cast<uint32_t*>(smem_raw) : hist + C::HIST_WORDS;
     __shared__ unsigned long long bars[C::NWARPS];
     __shared__ StreamCta cta;
 
@@ -849,7 +951,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     if ((p.flags & F_CARRY) && p.carry->status != 0) return;   // the stream already failed
     const unsigned long long line_base = (p.flags & F_CARRY) ? p.carry->line_base : p.line_base;
 
-    for (int i = tid; i < C::HIST_WORDS + C::LENH_WORDS; i += C::NTHREADS) hist[i] = 0;
+    for (int i = tid; i < C::BUF0 / 4; i += C::NTHREADS) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
     if (lane == 0) mbar_init(&bars[warp], 1);
     if (tid == 0) {
         cta.n_records = 0;
@@ -861,7 +963,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     fence_mbar_init();
     __syncthreads();
 
-    uint8_t* buf = smem_raw + C::HIST_WORDS * 4 + C::LENH_WORDS * 4 + warp * C::WARP_BYTES;
+    uint8_t* buf = smem_raw + C::BUF0 + warp * C::WARP_BYTES;
     uint16_t* list = reinterpret_cast<uint16_t*>(buf + C::WIN + 16);
     const uint32_t buf_s = smem_u32(buf);
     unsigned long long* bar = &bars[warp];
@@ -1381,7 +1483,7 @@ using SCfg10 = SCfg<10, 22, 2560>;   // P <= 320: 160 KB of counters, 22 warps x
 
 // the variable-length variants: same ranges (the host cuts the shard into grid x NWARPS of them), a spare row per chunk
 using VCfg5 = SCfg<5, 32, 4096, 1>;
-using VCfg10 = SCfg<10, 22, 2560, 1>;
+using VCfg10 = SCfg<10, 22, 4096, 1, 32>;   // rows 32 .. 127 only: 124 KB of counters leave room for 4 KiB windows
 static_assert(VCfg5::NWARPS == SCfg5::NWARPS && VCfg10::NWARPS == SCfg10::NWARPS, "both variants walk the same ranges");
 
 int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }

@@ -654,6 +654,59 @@ def test_clean_inputs_stay_on_the_fast_path(torch, oracle, eng, eng300):
                 assert_stats_equal(st, ost)
 
 
+def _var_recs(n, seed=0, lo=50, hi=300, head=b"r%d"):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), L))
+        qual = bytes(rng.integers(33, 127, L, dtype=np.uint8))
+        out.append(b"@" + (head % i) + b"\n" + seq + b"\n+\n" + qual + b"\n")
+    return out
+
+
+@pytest.mark.parametrize("what", ["clean", "tab_in_seq", "cr_in_qual", "nul_in_qual", "high_in_seq", "high_in_header",
+                                  "ctrl_in_header", "lengths_64k", "crlf", "clip"])
+def test_variable_length_variant(what, torch, oracle, eng, eng300):
+    """The speculative kernel's variant for reads of varying length (validate_block / line_steps; for P <= 320 its
+    table has no rows for bytes below 32): odd bytes in the sequence / quality lines must come out exact (through
+    the exact path), odd bytes in id lines must not matter, lengths at the 64-position step boundaries, '\r'
+    trimmed from one line only, reads longer than the tracked positions."""
+    recs = _var_recs(3000, seed=7)
+    if what == "lengths_64k":
+        recs = [_rec(i, L) for i, L in enumerate([0, 1, 3, 4, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 299, 300] * 60)]
+    elif what == "crlf":
+        recs = [_rec(i, L, crlf=(i % 3 == 0)) for i, L in enumerate([64, 65, 128, 50, 300, 129, 192] * 200)]
+        # '\r' in front of the '\n' of ONE of the two lines only: seq() and qual() differ in length by one
+        recs[5] = b"@x\n" + b"A" * 63 + b"\r\n+\n" + b"I" * 64 + b"\n"
+        recs[9] = b"@y\n" + b"C" * 128 + b"\n+\n" + b"I" * 127 + b"\r\n"
+    elif what == "clip":
+        recs = _var_recs(1500, seed=3, lo=250, hi=700)
+    k = 1234
+    def poke(line, byte):
+        parts = recs[k].split(b"\n")
+        parts[line] = parts[line][:20] + bytes([byte]) + parts[line][21:]
+        recs[k] = b"\n".join(parts)
+    if what == "tab_in_seq":
+        poke(1, 9)
+    elif what == "cr_in_qual":
+        poke(3, 13)
+    elif what == "nul_in_qual":
+        poke(3, 0)
+    elif what == "high_in_seq":
+        poke(1, 0xC3)
+    elif what == "high_in_header":
+        recs = [r.replace(b"@r", "@\u00e9\u4e2d".encode(), 1) for r in recs]
+    elif what == "ctrl_in_header":
+        recs = [r.replace(b"@r", b"@\t\x01", 1) for r in recs]
+    data = b"".join(recs)
+    for engine in (eng300, eng):
+        check_device_vs_oracle(torch, oracle, engine, data)
+        p = engine.last_path()
+        if what in ("clean", "high_in_header", "ctrl_in_header", "lengths_64k", "crlf", "clip"):
+            assert not p["exact"], (what, engine.max_len, p)          # served by the fast path
+
+
 def test_count_mode_varying_shapes(torch, oracle, eng):
     data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
     check_count_mode(torch, oracle, eng, data)
