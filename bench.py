@@ -36,15 +36,16 @@ GIB = 1 << 30
 
 
 def profiled_traffic(gib: float):
-    """dram read + write bytes per launch of the dominant kernel from the committed ncu --set full
+    """(dram read + write bytes per launch of the dominant kernel, source) from the committed ncu --set full
     capture (profiles/), valid for the workload it was captured on (16 GiB)."""
-    path = os.path.join(ROOT, "profiles", "r01_stream_kernel_ncu_full_16GiB.txt")
-    if abs(gib - 16.0) > 1e-9 or not os.path.exists(path):
-        return None
-    for line in open(path):
-        if line.startswith("traffic = dram read + write per launch"):
-            return float(line.split()[-1])
-    return None
+    for name in ("r02_stream_kernel_ncu_full_16GiB.txt", "r01_stream_kernel_ncu_full_16GiB.txt"):
+        path = os.path.join(ROOT, "profiles", name)
+        if abs(gib - 16.0) > 1e-9 or not os.path.exists(path):
+            continue
+        for line in open(path):
+            if line.startswith("traffic = dram read + write per launch"):
+                return float(line.split()[-1]), "ncu --set full, profiles/" + name
+    return None, None
 
 
 def peaks():
@@ -198,6 +199,60 @@ def workload_config(args, n_gpus):
             "l2": "inputs (GiBs) far larger than the 126 MB L2; no flush needed"}
 
 
+def sharded_bit_exact_check(fq, eng, sp, dist, world, rank, dev):
+    """Before anything is timed at N > 1: a small stream (cuts mid-record, a shard size that is no multiple of the
+    record size) parsed by the N ranks together -- NCCL all-reduce of [block | outcome slots] -- must give, bit
+    for bit, the statistics block and outcome of ONE parse of the whole stream on rank 0's GPU."""
+    import torch
+    from fastq_rs_b200.sharded import ShardSpec
+    shard = (6 << 20) + 4096 + 16 * 7                      # bytes per rank
+    total = world * shard // REC_BYTES * REC_BYTES
+    a, b = rank * shard, min(total, (rank + 1) * shard)
+    halo = min(total - b, fq._lib.MAX_RECORD_BYTES)
+    front = 16 if a > 0 else 0
+    buf = torch.empty(16 + (b - a) + halo + 64, dtype=torch.uint8, device=dev)
+    eng.synth_fixed(buf.data_ptr() + 16 - front, (b - a) + halo + front, byte_off=a - front, read_len=READ_LEN)
+    idx = torch.empty(4 * ((b - a) // REC_BYTES + 4), dtype=torch.int32, device=dev)
+    c0 = sp.collectives
+    out, st = sp.parse(ShardSpec(buf[16 - front:], a, b, halo, front, is_last=(b + halo == total)), hist=True, index=idx)
+    assert sp.collectives - c0 == 1 and sp.reparsed == 0, "the common case is one collective"
+    ok = torch.ones(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        whole = torch.empty(total + 64, dtype=torch.uint8, device=dev)
+        eng.synth_fixed(whole, total, read_len=READ_LEN)
+        eng.parse_device(whole, n_own=total, n_avail=total, hist=True)
+        out1, st1 = eng.fetch()
+        same = (out.status, out.n_records, out.n_lines, out.finished) == (out1.status, out1.n_records, out1.n_lines, out1.finished)
+        same = same and bool(np.array_equal(st.words, st1.words)) and out1.n_records == total // REC_BYTES
+        ok[0] = 1 if same else 0
+    dist.broadcast(ok, src=0)
+    assert int(ok.item()) == 1, "N-rank result differs from the single-GPU parse of the same stream"
+    return {"bytes": total, "records": total // REC_BYTES, "words_compared": int(st.words.size), "collectives": 1}
+
+
+def time_config(eng, torch, steps, warmup, parse, n_bytes, n_rec, peak, index_entries):
+    """One BASELINE configuration on one GPU: (GB/s over whole steps, kernel ms, roofline fraction)."""
+    for _ in range(max(1, warmup)):
+        parse()
+        out, _ = eng.fetch()
+    assert out.status == 0 and out.n_records == n_rec, out
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = []
+    e0.record()
+    for _ in range(steps):
+        parse()
+        eng.fetch()
+        k.append(eng.last_scan_ms())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    k_ms = float(np.mean(k))
+    alg = n_bytes + 4 * index_entries
+    return {"value": n_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "kernel_ms": k_ms,
+            "algorithmic_bytes": alg, "roofline_frac": alg / (k_ms * 1e-3) / 1e9 / peak, "records": n_rec}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,6 +266,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = f"cuda:{local}"
     eng = fq.Engine(max_len=READ_LEN, device=local, slot_bytes=args.slot_mib << 20, n_slots=3)
+    peak, peak_src = peaks()
 
     # ---- the stream: world x gib GiB of synthetic input A, sharded by byte chunk ------------
     shard = int(args.gib * GIB) // 16 * 16
@@ -226,15 +282,16 @@ def run_ours(args):
     index = torch.empty(4 * n_rec_upper, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
-    # N > 1: the N-rank driver (fastq_rs_b200/sharded.py): every rank parses its shard at once with an
-    # inferred start, one all-gather of a few words per rank confirms the line numbers, one all_reduce
-    # of the statistics block -- no byte is read twice and nothing else crosses NVLink
+    # N > 1: every rank parses its shard at once with an inferred start; ONE all-reduce of [statistics block |
+    # outcome slots] (the library's own NCCL call, fqb_allreduce) both sums the statistics and gathers the
+    # outcomes that confirm the inferred line numbers; one device-to-host copy.  No byte is read twice.
     from fastq_rs_b200.sharded import ShardedParser, ShardSpec
     sp = ShardedParser(eng, dist=dist if world > 1 else None, device=dev)
     spec = ShardSpec(buf[16 - front:], a, b, halo, front, is_last=(b + halo == total))
+    check = sharded_bit_exact_check(fq, eng, sp, dist, world, rank, dev) if world > 1 else None
 
     def step():
-        """One pass of the hot path over this rank's shard (+ the exchange steps when sharded)."""
+        """One pass of the hot path over this rank's shard (+ the one collective when sharded)."""
         if world > 1:
             return sp.parse(spec, hist=True, index=index)
         eng.parse_device(data, n_own=n_own, n_avail=n_avail, hist=True, index=index, line_base=0,
@@ -255,6 +312,7 @@ def run_ours(args):
 
     # ---- timed region: HBM-resident ---------------------------------------------------------
     launches0 = eng.launch_count()
+    coll0 = sp.collectives
     scan_ms = []
     with ClockSampler(local) as clk:
         barrier()
@@ -273,16 +331,48 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     value = total / (ms_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (fq_scan_kernel), live CUDA events on its stream -----
-    peak, peak_src = peaks()
+    # ---- roofline of the dominant kernel, live CUDA events on its stream ----------------------
     k_ms = float(np.mean(scan_ms))
     alg_bytes = n_own + 16 * (n_own // REC_BYTES)            # 1 B read per input byte + 16 B index per record
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5>>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak,
-                "traffic": args.traffic_bytes if args.traffic_bytes is not None else profiled_traffic(args.gib),
-                "traffic_source": "ncu --set full, profiles/r01_stream_kernel_ncu_full_16GiB.txt", "peak_source": peak_src,
+    traffic, traffic_src = profiled_traffic(args.gib)
+    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5,32,4096>, HIST, predicting variant>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": args.traffic_bytes if args.traffic_bytes is not None else traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes}
+
+    # ---- every BASELINE configuration, one GPU each (N = 1 line only) --------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        n_rec = n_own // REC_BYTES
+        cs, cw = max(3, min(args.steps, 5)), 2
+
+        def dev_parse(hist, idx):
+            return lambda: eng.parse_device(data, n_own=n_own, n_avail=n_avail, hist=hist, index=idx)
+        configs = []
+        for name, hist, idx in (("configs[1]: delimit + record count", False, None),
+                                ("configs[1]': delimit + line-end index", False, index),
+                                ("configs[2]: per-position ACGTN + quality histograms", True, None),
+                                ("configs[1]+[2] fused: delimit + index + histograms (the headline)", True, index)):
+            c = time_config(eng, torch, cs, cw, dev_parse(hist, idx), n_own, n_rec, peak, 4 * n_rec if idx is not None else 0)
+            c["workload"] = f"{args.gib:g} GiB fixed 150 bp, {name}"
+            configs.append(c)
+        # configs[3]: variable 50-300 bp (P = 300), same bytes per GPU
+        del index
+        eng3 = fq.Engine(max_len=300, device=local)
+        n_var = int(args.gib * GIB / 371.3)
+        vbuf, vbytes = eng3.synth_var(n_var, pad=64)
+        vidx = torch.empty(4 * n_var + 8, dtype=torch.int32, device=dev)
+        for name, hist, idx in (("configs[3]: delimit + index + histograms", True, vidx),
+                                ("configs[3]': delimit + index", False, vidx)):
+            c = time_config(eng3, torch, cs, cw, (lambda h=hist, i=idx: eng3.parse_device(vbuf, n_own=vbytes, n_avail=vbytes, hist=h, index=i)),
+                            vbytes, n_var, peak, 4 * n_var)
+            c["workload"] = f"{vbytes / GIB:.2f} GiB variable-length 50-300 bp, {name}"
+            configs.append(c)
+        eng3.close()
+        del vbuf, vidx
+        index = torch.empty(4 * n_rec_upper, dtype=torch.int32, device=dev)
 
     # ---- end to end through the host API (rank-local; pinned host bytes) ---------------------
     e2e = None
@@ -298,6 +388,11 @@ def run_ours(args):
             "config": workload_config(args, world), "roofline": roofline, "clocks": clk.summary(),
             "gpu_launches": int(launches), "records": total // REC_BYTES,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if world > 1:
+            line["collectives_per_step"] = (sp.collectives - coll0) / args.steps
+            line["sharded_check"] = check
     if e2e is not None:
         ev = torch.tensor([e2e["bytes"], e2e["seconds"]], dtype=torch.float64, device=dev)
         if world > 1:
@@ -311,8 +406,8 @@ def run_ours(args):
                            "h2d_bytes_per_step": int(e2e["bytes"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "bytes_per_gpu": int(e2e["bytes"]), "api": "fqb_parse_host(FQB_F_HIST | FQB_F_INDEX): pinned ring of 3 slots; outcome, statistics block and the "
                                   "line-end index (pinned buffer) all land on the host",
-                           "sample": f"{e2e['bytes'] / GIB:.2f} GiB prefix of each rank's shard, pinned host memory"}
-    if rank == 0 and world == 1 and not args.no_cpu:
+                           "sample": f"{e2e['bytes'] / GIB:.2f} GiB of each rank's shard, pinned host memory"}
+    if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         workers = max(1, cores - 1)
         sample = gen_host_sample(int(args.cpu_sample_gib * GIB), cores)
@@ -321,6 +416,8 @@ def run_ours(args):
             "value": v, "unit": "GB/s", "cores": workers + 1, "kind": "port",
             "sample": f"{sample.size / GIB:.2f} GiB prefix of the same synthetic stream, host RAM, best of 2; "
                       f"oracle parallel_each({workers}) + stats closure"}
+    if world > 1:
+        dist.barrier()
     if rank == 0:
         print(json.dumps(line))
     eng.close()
@@ -382,19 +479,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=16.0, help="GiB of FASTQ per GPU")
     ap.add_argument("--e2e-gib", type=float, default=None,
-                    help="GiB per GPU streamed from pinned host memory in the e2e leg (PCIe-bound: the rate does not "
-                         "depend on the size); default: the whole 16 GiB shard at N=1, a 4 GiB prefix of every shard at N>1 "
-                         "(keeps pinning time and pinned host RAM bounded at N=8)")
+                    help="GiB per GPU streamed from pinned host memory in the e2e leg; default: the whole shard of every "
+                         "rank (halved until the pinned allocation succeeds, and reported)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--slot-mib", type=int, default=64)
     ap.add_argument("--cpu-sample-gib", type=float, default=2.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration list (N = 1 line)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes/launch from the committed ncu --set full capture (profiles/)")
     args = ap.parse_args()
     if args.e2e_gib is None:
-        args.e2e_gib = 16.0 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 4.0
+        args.e2e_gib = args.gib
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

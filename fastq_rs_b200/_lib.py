@@ -15,7 +15,8 @@ ABI_VERSION = int(os.environ.get("FQB_ABI", "3"))   # (FQB_ABI: A/B runs against
 
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
-E_ARG, E_STATE, E_NOMEM, E_CUDA = 50, 51, 52, 100
+E_ARG, E_STATE, E_NOMEM, E_CUDA, E_NCCL = 50, 51, 52, 100, 101
+MAX_WORLD, COMM_ID_BYTES = 64, 128
 KEEP_ALL, KEEP_DNA, KEEP_DNAN = 0, 1, 2
 F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START, F_PARTIAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 MAX_RECORD_BYTES = 68 * 1024
@@ -31,6 +32,8 @@ SYMBOLS = [
     "fqb_stream_begin", "fqb_stream_acquire", "fqb_stream_submit", "fqb_stream_finish",
     "fqb_host_alloc", "fqb_host_free", "fqb_synth_fixed_device", "fqb_synth_var_device",
     "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter", "fqb_last_path",
+    "fqb_comm_unique_id", "fqb_comm_init", "fqb_comm_destroy", "fqb_comm_rank", "fqb_comm_world", "fqb_allreduce",
+    "fqb_fetch_reduced", "fqb_device_exchange", "fqb_exchange_words",
 ]
 
 
@@ -130,6 +133,21 @@ def lib():
     L.fqb_synth_var_sizes_device.restype = i32
     L.fqb_last_path.argtypes = [vp, C.POINTER(u64 * 3)]
     L.fqb_last_path.restype = i32
+    L.fqb_comm_unique_id.argtypes = [vp]
+    L.fqb_comm_unique_id.restype = i32
+    L.fqb_comm_init.argtypes = [vp, i32, i32, vp]
+    L.fqb_comm_init.restype = i32
+    for n in ("fqb_comm_destroy", "fqb_comm_rank", "fqb_comm_world"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = i32
+    L.fqb_allreduce.argtypes = [vp, vp]
+    L.fqb_allreduce.restype = i32
+    L.fqb_fetch_reduced.argtypes = [vp, vp, vp, vp]
+    L.fqb_fetch_reduced.restype = i32
+    L.fqb_device_exchange.argtypes = [vp]
+    L.fqb_device_exchange.restype = vp
+    L.fqb_exchange_words.argtypes = [vp]
+    L.fqb_exchange_words.restype = C.c_size_t
     L.fqb_filter_device.argtypes = [vp, vp, u64, vp, u64, u64, u32, vp, u64, vp]
     L.fqb_filter_device.restype = i32
     L.fqb_fetch_filter.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64)]

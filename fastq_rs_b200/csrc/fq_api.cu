@@ -8,6 +8,8 @@
 #include "../../include/fastq_b200.h"
 #include "fq_common.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -118,7 +120,11 @@ struct fqb_ctx {
     int grid = 148;
     size_t nwords = 0;
     // one-shot / per-chunk device state
-    uint64_t* d_stats = nullptr;
+    uint64_t* d_stats = nullptr;      // [statistics block (nwords) | FQB_MAX_WORLD x 8 outcome words, one slot per rank]
+    uint64_t* d_reduced = nullptr;    // the same layout after fqb_allreduce
+    uint64_t* h_reduced = nullptr;    // pinned
+    int rank = 0, world = 1;          // fqb_comm_init
+    void* nccl_comm = nullptr;
     uint64_t* d_seqraw = nullptr;
     DevResult* d_res = nullptr;
     unsigned long long* d_pub = nullptr;   // outcome of the last parse as 8 device words (fqb_device_result)
@@ -244,7 +250,9 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     CKC(scan_configure());
     CKC(stream_configure());
     ctx->grid = ctx->num_sms * scan_blocks_per_sm(ctx->nchunk);
-    CKC(cudaMalloc(&ctx->d_stats, ctx->nwords * 8));
+    CKC(cudaMalloc(&ctx->d_stats, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8));   // [block | 8 outcome words per rank]
+    CKC(cudaMalloc(&ctx->d_reduced, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8));
+    CKC(cudaHostAlloc(&ctx->h_reduced, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8, cudaHostAllocDefault));
     CKC(cudaMalloc(&ctx->d_seqraw, (size_t)ctx->P * 256 * 8));
     CKC(cudaMalloc(&ctx->d_res, sizeof(DevResult)));
     CKC(cudaMalloc(&ctx->d_ranges, sizeof(RangeInfo) * ctx->grid));
@@ -294,7 +302,10 @@ void fqb_destroy(fqb_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     stream_free(ctx);
+    fqb_comm_destroy(ctx);
     cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_reduced);
+    if (ctx->h_reduced) cudaFreeHost(ctx->h_reduced);
     cudaFree(ctx->d_seqraw);
     cudaFree(ctx->d_res);
     cudaFree(ctx->d_ranges);
@@ -394,7 +405,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     fq_init_kernel<<<1, 32, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3), sh->d_bytes, sh->n_avail,
                                      (fast && (sh->flags & FQB_F_HIST) && !getenv("FQB_NO_VAR")) ? 1 : 0);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(ctx->d_stats, 0, ctx->nwords * 8, st));
+    CK(cudaMemsetAsync(ctx->d_stats, 0, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8, st));   // block + outcome slots
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
     ctx->launches += 1;
     if (p.ntiles) {
@@ -436,7 +447,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             ctx->launches += 1;
         }
     }
-    CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), carry ? nullptr : ctx->d_pub, st));
+    CK(launch_finalize(p, carry, reinterpret_cast<unsigned long long*>(total), carry ? nullptr : ctx->d_pub,
+                       carry ? nullptr : reinterpret_cast<unsigned long long*>(ctx->d_stats) + ctx->nwords + 8 * (size_t)ctx->rank, st));
     ctx->launches += 1;
     return FQB_OK;
 }
@@ -891,6 +903,131 @@ int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint64_t stre
     ctx->host_index_dev = nullptr;
     ctx->host_index_cap = 0;
     return rc;
+}
+
+
+// ==========================================================================================
+// N ranks, one byte shard each: the ONE collective of the path behind the ABI
+// ==========================================================================================
+// NCCL is bound at run time (dlopen): a process that already carries a libnccl.so.2 (PyTorch's) shares it, a
+// plain C / Rust caller gets the system one, and single-GPU users need none at all.  Only entry points whose
+// signatures have been stable across NCCL 2.x are used.
+namespace {
+struct NcclApi {
+    struct Id128 {                      // ncclUniqueId (passed by value)
+        char b[FQB_COMM_ID_BYTES];
+    };
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const char* nccl_load()
+{
+    if (g_nccl.h) return nullptr;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return "libnccl.so.2 not found";
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return "libnccl: missing symbols";
+    g_nccl.h = h;
+    return nullptr;
+}
+int nccl_fail(fqb_ctx* ctx, int rc, const char* what)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+    ctx->err = buf;
+    return FQB_E_NCCL;
+}
+}  // namespace
+
+int fqb_comm_unique_id(uint8_t out[FQB_COMM_ID_BYTES])
+{
+    if (!out) return FQB_E_ARG;
+    if (nccl_load()) return FQB_E_NCCL;
+    return g_nccl.GetUniqueId(out) == 0 ? FQB_OK : FQB_E_NCCL;
+}
+
+int fqb_comm_init(fqb_ctx* ctx, int rank, int world, const uint8_t id[FQB_COMM_ID_BYTES])
+{
+    if (!ctx || world < 1 || world > FQB_MAX_WORLD || rank < 0 || rank >= world) return FQB_E_ARG;
+    if (ctx->nccl_comm) return FQB_E_STATE;
+    if (world > 1) {
+        if (!id) return FQB_E_ARG;
+        if (const char* e = nccl_load()) {
+            ctx->err = e;
+            return FQB_E_NCCL;
+        }
+        CK(cudaSetDevice(ctx->device));
+        NcclApi::Id128 uid;
+        memcpy(uid.b, id, sizeof uid.b);
+        void* comm = nullptr;
+        const int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+        if (rc != 0) return nccl_fail(ctx, rc, "ncclCommInitRank");
+        ctx->nccl_comm = comm;
+    }
+    ctx->rank = rank;
+    ctx->world = world;
+    return FQB_OK;
+}
+
+int fqb_comm_destroy(fqb_ctx* ctx)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        g_nccl.CommDestroy(ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->rank = 0;
+    ctx->world = 1;
+    return FQB_OK;
+}
+
+int fqb_comm_rank(fqb_ctx* ctx) { return ctx ? ctx->rank : -1; }
+int fqb_comm_world(fqb_ctx* ctx) { return ctx ? ctx->world : -1; }
+
+uint64_t* fqb_device_exchange(fqb_ctx* ctx) { return ctx ? ctx->d_stats : nullptr; }
+size_t fqb_exchange_words(fqb_ctx* ctx) { return ctx ? ctx->nwords + 8 * (size_t)ctx->world : 0; }
+
+int fqb_allreduce(fqb_ctx* ctx, void* stream)
+{
+    if (!ctx) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = ctx->nwords + 8 * (size_t)ctx->world;
+    if (ctx->world == 1) {
+        CK(cudaMemcpyAsync(ctx->d_reduced, ctx->d_stats, n * 8, cudaMemcpyDeviceToDevice, st));
+        return FQB_OK;
+    }
+    if (!ctx->nccl_comm) return FQB_E_STATE;
+    const int rc = g_nccl.AllReduce(ctx->d_stats, ctx->d_reduced, n, 5 /* ncclUint64 */, 0 /* ncclSum */, ctx->nccl_comm, st);
+    if (rc != 0) return nccl_fail(ctx, rc, "ncclAllReduce");
+    return FQB_OK;
+}
+
+int fqb_fetch_reduced(fqb_ctx* ctx, void* stream, uint64_t* host_stats, uint64_t* outcomes)
+{
+    if (!ctx) return FQB_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = ctx->nwords + 8 * (size_t)ctx->world;
+    // (the outcome slots first: a caller that only wants them -- the common case checks them before it looks at
+    // the block -- still pays one copy, one synchronisation)
+    CK(cudaMemcpyAsync(ctx->h_reduced, ctx->d_reduced, n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (host_stats) memcpy(host_stats, ctx->h_reduced, ctx->nwords * 8);
+    if (outcomes) memcpy(outcomes, ctx->h_reduced + ctx->nwords, 8 * (size_t)ctx->world * 8);
+    return FQB_OK;
 }
 
 }  // extern "C"

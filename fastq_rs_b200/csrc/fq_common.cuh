@@ -149,7 +149,7 @@ cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStrea
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st);
 cudaError_t launch_tail_index(const ScanParams& p, DevCarry* carry, cudaStream_t st);
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, unsigned long long* pub,
-                            cudaStream_t st);
+                            unsigned long long* slot, cudaStream_t st);
 cudaError_t launch_count(const uint8_t* d, unsigned long long n, unsigned long long* out, int grid, cudaStream_t st);
 cudaError_t launch_synth_fixed(uint8_t* out, unsigned long long n, unsigned long long byte_off, uint32_t L,
                                unsigned long long seed, cudaStream_t st);

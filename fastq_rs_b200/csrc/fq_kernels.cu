@@ -160,7 +160,7 @@ __global__ void fq_range_prefix_kernel(const ScanParams p, const DevCarry* carry
 // fold the raw sequence-byte histogram into the six base classes (validate_dnan's alphabet,
 // src/records.rs:29-33), publish the outcome, and (streaming) add the chunk into the totals
 __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned long long* total,
-                                   unsigned long long* pub)
+                                   unsigned long long* pub, unsigned long long* slot)
 {
     const uint32_t P = p.max_len;
     const bool skip = carry && carry->status != 0;  // stream failed in an earlier chunk
@@ -209,6 +209,10 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
                 pub[5] = r->tail_start == NONE64 ? NONE64 : p.stream_offset + r->tail_start;
                 pub[6] = (unsigned long long)r->line_phase;
                 pub[7] = 0;
+                // the same words in this rank's slot behind the statistics block: all other slots are zero, so the
+                // all-reduce(sum) of [block | slots] is at the same time the all-gather of the outcomes
+                if (slot)
+                    for (int k = 0; k < 8; ++k) slot[k] = pub[k];
             }
             if (carry) {
                 carry->n_records += p.stats[0];
@@ -440,9 +444,9 @@ cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges
 }
 
 cudaError_t launch_finalize(const ScanParams& p, DevCarry* carry, unsigned long long* total, unsigned long long* pub,
-                            cudaStream_t st)
+                            unsigned long long* slot, cudaStream_t st)
 {
-    fq_finalize_kernel<<<64, 256, 0, st>>>(p, carry, total, pub);
+    fq_finalize_kernel<<<64, 256, 0, st>>>(p, carry, total, pub, slot);
     return cudaGetLastError();
 }
 

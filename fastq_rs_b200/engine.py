@@ -163,6 +163,42 @@ class Engine:
             self._result_view = self._device_view(self.L.fqb_device_result(self.ctx), 8)
         return self._result_view
 
+    # ---- N ranks: the one collective, behind the ABI (NCCL bound by the library itself) ------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+        _check(self.ctx, self.L.fqb_comm_unique_id(buf), "fqb_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, rank: int, world: int, uid: bytes | None = None) -> None:
+        """collective over all ranks; `uid` = rank 0's comm_unique_id(), handed around by the caller"""
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(uid) if uid is not None else None
+        _check(self.ctx, self.L.fqb_comm_init(self.ctx, rank, world, buf), "fqb_comm_init")
+        self._xchg_view = None
+
+    def comm_world(self) -> int:
+        return int(self.L.fqb_comm_world(self.ctx))
+
+    def allreduce(self, stream=None) -> None:
+        """enqueue the all-reduce(sum, u64) of [statistics block | world x 8 outcome words] of the last parse"""
+        _check(self.ctx, self.L.fqb_allreduce(self.ctx, self._stream_ptr(stream)), "fqb_allreduce")
+
+    def fetch_reduced(self, want_stats: bool = True, stream=None):
+        """wait for allreduce(): (global stats words | None, outcomes[world, 8]) -- one copy, one synchronisation"""
+        world = self.comm_world()
+        words = np.zeros(self.n_words, dtype=np.uint64) if want_stats else None
+        outs = np.zeros(8 * world, dtype=np.uint64)
+        _check(self.ctx, self.L.fqb_fetch_reduced(self.ctx, self._stream_ptr(stream),
+                                                  words.ctypes.data if want_stats else None, outs.ctypes.data),
+               "fqb_fetch_reduced")
+        return words, outs.view(np.int64).reshape(world, 8)
+
+    def device_exchange(self):
+        """[statistics block | world x 8 outcome words] of the last parse as an int64 CUDA tensor view -- the
+        send buffer of the one collective, for callers that run it with their own library"""
+        if getattr(self, "_xchg_view", None) is None:
+            self._xchg_view = self._device_view(self.L.fqb_device_exchange(self.ctx), int(self.L.fqb_exchange_words(self.ctx)))
+        return self._xchg_view
+
     def count_lines(self, d_bytes, n: int | None = None, stream=None) -> int:
         n = d_bytes.numel() if n is None else n
         sp = self._stream_ptr(stream)

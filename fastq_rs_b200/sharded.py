@@ -14,11 +14,13 @@ this is the B200-side answer to "the path shards by byte chunk" 
     never depends on the inference, and in the common case no byte is read twice;
   * errors: the first bad record in stream order wins (Parser::each delivers everything before it,
     src/lib.rs:226-237): shards behind it contribute nothing;
-  * ONE all_reduce(sum) of the u64 statistics block.
+  * ONE all_reduce(sum) of [u64 statistics block | world x 8 outcome words]: every rank writes its outcome into
+    its own slot, so the reduction is also the gather that confirms the inferred line phases.
 
-`torch.distributed` is plumbing only (NCCL on the GPUs, gloo in the CPU tests).  The engine object
-is duck-typed (`parse_device`, `fetch`, `device_stats`) so that the protocol can be tested on CPU
-with a stand-in; the product engine is `fastq_rs_b200.Engine`.
+With the product engine (`fastq_rs_b200.Engine`) the collective is the library's own: NCCL bound behind the
+C ABI (fqb_comm_init / fqb_allreduce / fqb_fetch_reduced), `torch.distributed` only carries the ncclUniqueId to
+the other ranks.  The engine object is duck-typed so that the protocol can be tested on CPU with a stand-in
+whose send buffer is reduced over gloo.
 """
 from __future__ import annotations
 
@@ -57,6 +59,12 @@ class ShardSpec:
 
 
 class ShardedParser:
+    """Glue around the engine's N-rank entry points.  Per step, in the common case: parse (enqueued), ONE
+    all-reduce of [statistics block | world x 8 outcome words] (each rank's outcome sits in its own slot, so the
+    sum is also the gather), ONE device-to-host copy.  With the product engine the collective is the library's
+    own (fqb_allreduce: NCCL bound behind the C ABI); a duck-typed engine without it (the CPU tests' stand-in over
+    gloo) has the same buffer reduced through torch.distributed."""
+
     def __init__(self, engine, dist=None, group=None, device=None):
         self.eng = engine
         self.dist = dist
@@ -65,32 +73,46 @@ class ShardedParser:
         self.rank = dist.get_rank(group) if dist is not None else 0
         self.world = dist.get_world_size(group) if dist is not None else 1
         self.reparsed = 0   # shards parsed twice so far (inference not confirmed)
+        self.collectives = 0
+        self.native = hasattr(engine, "allreduce")
+        if self.native and engine.comm_world() != self.world:
+            self._comm_init()
+        elif hasattr(engine, "set_rank"):
+            engine.set_rank(self.rank, self.world)
 
-    # -- collectives (a few words per rank; the stats block) ---------------------------------
-    def _all_gather_words(self, words: list[int]) -> np.ndarray:
+    def _comm_init(self):
+        """hand rank 0's ncclUniqueId to the other ranks (torch.distributed is only the messenger)"""
         import torch
-        mine = torch.tensor(words, dtype=torch.int64, device=self.device)
-        if self.dist is None or self.world == 1:
-            return mine.cpu().numpy().reshape(1, -1)
-        out = torch.empty(self.world * len(words), dtype=torch.int64, device=self.device)
-        self.dist.all_gather_into_tensor(out, mine, group=self.group)
-        return out.cpu().numpy().reshape(self.world, -1)
+        uid = torch.zeros(128, dtype=torch.uint8, device=self.device)
+        if self.world > 1:
+            if self.rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(self.eng.comm_unique_id()), dtype=torch.uint8))
+            self.dist.broadcast(uid, src=0, group=self.group)
+        self.eng.comm_init(self.rank, self.world, bytes(uid.cpu().numpy().tobytes()) if self.world > 1 else None)
 
-    def _parse(self, sh: ShardSpec, hist, index, line_base, infer):
-        view = sh.data[sh.front:] if sh.front else sh.data
-        if sh.b == sh.a:   # an empty shard (more ranks than 16-byte pieces): nothing to own, nothing to read
-            self.eng.parse_device(view, n_own=0, n_avail=0, hist=hist, index=None, line_base=line_base,
-                                  stream_offset=sh.a, line_start=False, front16=False, eof=sh.is_last)
-            return self.eng.fetch(want_stats=False)[0]
-        self.eng.parse_device(view, n_own=sh.b - sh.a, n_avail=sh.b - sh.a + sh.halo, hist=hist, index=index,
-                              line_base=line_base, stream_offset=sh.a, line_start=(sh.a == 0),
-                              front16=(sh.front == 16), eof=sh.is_last, infer_start=infer)
-        return self.eng.fetch(want_stats=False)[0]
+    # -- the one collective -----------------------------------------------------------------------
+    def _reduce(self, want_stats=True):
+        """(global stats words | None, outcomes[world, 8]) of the parse enqueued last"""
+        self.collectives += 1
+        if self.native:
+            self.eng.allreduce()
+            return self.eng.fetch_reduced(want_stats=want_stats)
+        x = self.eng.device_exchange().clone()
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(x, op=self.dist.ReduceOp.SUM, group=self.group)
+        h = x.cpu().numpy()
+        nw = h.size - 8 * self.world
+        return (h[:nw].view(np.uint64).copy() if want_stats else None), h[nw:].reshape(self.world, 8)
+
+    def _my_slot(self):
+        x = self.eng.device_exchange()
+        nw = x.numel() - 8 * self.world
+        return x[nw + 8 * self.rank: nw + 8 * self.rank + 8]
 
     def _enqueue(self, sh: ShardSpec, hist, index, line_base, infer):
         """parse_device without waiting for it"""
         view = sh.data[sh.front:] if sh.front else sh.data
-        if sh.b == sh.a:
+        if sh.b == sh.a:   # an empty shard (more ranks than 16-byte pieces): nothing to own, nothing to read
             self.eng.parse_device(view, n_own=0, n_avail=0, hist=hist, index=None, line_base=line_base,
                                   stream_offset=sh.a, line_start=False, front16=False, eof=sh.is_last)
         else:
@@ -101,78 +123,55 @@ class ShardedParser:
     def parse(self, sh: ShardSpec, hist: bool = True, index=None):
         """Delimit (+histograms) the whole stream; every rank returns the GLOBAL (Outcome, Stats).
         `index` (optional int32 tensor) receives this rank's line ends (low 32 bits of the stream
-        offsets of the '\n' in [a, b)).
-
-        Common case = ONE host synchronisation: the parse, an all-gather of the 8-word device-resident
-        outcomes, and an all-reduce of a copy of the statistics block are enqueued back to back; the
-        host then reads both.  Only if some outcome shows an error, an unconfirmed inference or
-        FQB_E_PHASE is the careful path below taken (the local statistics block is still intact)."""
-        import torch
+        offsets of the '\n' in [a, b))."""
         infer = sh.a != 0 and sh.b > sh.a
-        fast = hasattr(self.eng, "device_result") and self.dist is not None and self.world > 1
-        if fast:
-            self._enqueue(sh, hist, index, 0, infer)
-            res_all = torch.empty(self.world * 8, dtype=torch.int64, device=self.device)
-            self.dist.all_gather_into_tensor(res_all, self.eng.device_result(), group=self.group)
-            summed = self.eng.device_stats().clone()
-            self.dist.all_reduce(summed, op=self.dist.ReduceOp.SUM, group=self.group)
-            g8 = res_all.cpu().numpy().reshape(self.world, 8)          # the one synchronisation
-            lb = np.concatenate([[0], np.cumsum(g8[:-1, 3])])          # exact line numbers: prefix of n_lines
-            if bool((g8[:, 0] == OK).all()) and self._phases_ok(g8, lb):
-                words = summed.cpu().numpy().view(np.uint64).copy()
-                total = Outcome(status=OK, finished=bool(g8[-1, 1]), n_records=int(g8[:, 2].sum()),
-                                n_lines=int(g8[:, 3].sum()), err_offset=0, tail_offset=None, line_phase=0)
-                return total, Stats(self.eng.max_len, words)
-            out = self.eng.fetch(want_stats=False)[0]
-        else:
-            out = self._parse(sh, hist, index, 0, infer)
-        return self._careful(sh, hist, index, infer, out)
+        self._enqueue(sh, hist, index, 0, infer)
+        words, g = self._reduce()
+        lb = np.concatenate([[0], np.cumsum(g[:-1, 3])])            # exact line numbers: prefix of the n_lines
+        if bool((g[:, 0] == OK).all()) and self._phases_ok(g, lb):
+            total = Outcome(status=OK, finished=bool(g[-1, 1]), n_records=int(g[:, 2].sum()),
+                            n_lines=int(g[:, 3].sum()), err_offset=0, tail_offset=None, line_phase=0)
+            return total, Stats(self.eng.max_len, words)
+        return self._careful(sh, hist, index, infer, g, lb)
 
-    def _phases_ok(self, g8, lb) -> bool:
+    def _phases_ok(self, g, lb) -> bool:
         """every inferring shard (all but the first, unless it owns nothing) reports the phase its exact
         line number has; shards that own nothing (n_lines == 0 and n_records == 0) are exempt"""
         for r in range(1, self.world):
-            empty = g8[r, 3] == 0 and g8[r, 2] == 0
-            if not empty and (int(g8[r, 6]) & 3) != (int(lb[r]) & 3):
+            empty = g[r, 3] == 0 and g[r, 2] == 0
+            if not empty and (int(g[r, 6]) & 3) != (int(lb[r]) & 3):
                 return False
         return True
 
-    def _careful(self, sh, hist, index, infer, out):
-        """The general protocol: confirm or redo the inference, first error in stream order wins."""
-        def words(o):
-            return [o.status, o.err_offset, o.n_records, o.n_lines, int(o.finished), o.line_phase]
-        g = self._all_gather_words(words(out))
-        line_base = int(g[:self.rank, 3].sum())        # exact line number of this shard: prefix of n_lines
+    def _careful(self, sh, hist, index, infer, g, lb):
+        """Some outcome shows an error, an unconfirmed inference or FQB_E_PHASE: confirm or redo the
+        inferences, first error in stream order wins.  Every rank holds all outcomes, so every rank takes the
+        same decisions without further messages; one more reduction at the end."""
         if bool((g[:, 0] == E_PHASE).any()):
             # some shard could not even deliver its newline count: every rank counts (one cheap pass)
             view = sh.data[sh.front:] if sh.front else sh.data
             n = self.eng.count_lines(view, sh.b - sh.a) if sh.b > sh.a else 0
-            g2 = self._all_gather_words([n])
-            line_base = int(g2[:self.rank, 0].sum())
-        unconfirmed = infer and (out.status == E_PHASE or out.line_phase != (line_base & 3))
-        if unconfirmed:
-            # the inference is not confirmed: parse again with the exact line number
-            self.reparsed += 1
-            out = self._parse(sh, hist, index, line_base, False)
-        # did anybody parse again?  (every rank can tell from the gathered phases and counts)
-        lb = np.concatenate([[0], np.cumsum(g[:-1, 3])]) if not bool((g[:, 0] == E_PHASE).any()) else None
-        anybody = bool((g[:, 0] == E_PHASE).any()) or bool(((g[1:, 5] & 3) != (lb[1:] & 3)).any())
-        if anybody:
-            g = self._all_gather_words(words(out))
+            self._my_slot()[3] = n          # (my outcome's n_lines word in the send buffer)
+            _, g2 = self._reduce(want_stats=False)
+            lb = np.concatenate([[0], np.cumsum(g2[:-1, 3])])
+        line_base = int(lb[self.rank])
+        mine = g[self.rank]
+        if infer and (int(mine[0]) == E_PHASE or (int(mine[6]) & 3) != (line_base & 3)):
+            self.reparsed += 1      # the inference is not confirmed: parse again with the exact line number
+            self._enqueue(sh, hist, index, line_base, False)
+        # (a rank that does not parse again still has its block and outcome in the send buffer)
+        _, g = self._reduce(want_stats=False)
         # first error in stream order wins; shards behind it contribute nothing
         bad = np.nonzero(g[:, 0] != OK)[0]
         first_bad = int(bad[0]) if bad.size else None
-        stats_dev = self.eng.device_stats()
         if first_bad is not None and self.rank > first_bad:
-            stats_dev.zero_()
-        if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(stats_dev, op=self.dist.ReduceOp.SUM, group=self.group)
-        stats_words = stats_dev.cpu().numpy().view(np.uint64).copy()
+            self.eng.device_stats().zero_()
+        words, _ = self._reduce()
         upto = self.world if first_bad is None else first_bad + 1
         total = Outcome(status=int(g[first_bad, 0]) if first_bad is not None else OK,
-                        finished=first_bad is None and bool(g[-1, 4]),
+                        finished=first_bad is None and bool(g[-1, 1]),
                         n_records=int(g[:upto, 2].sum()),
                         n_lines=int(g[:, 3].sum()),
-                        err_offset=int(g[first_bad, 1]) if first_bad is not None else 0,
+                        err_offset=int(g[first_bad, 4]) if first_bad is not None else 0,
                         tail_offset=None, line_phase=0)
-        return total, Stats(self.eng.max_len, stats_words)
+        return total, Stats(self.eng.max_len, words)

@@ -39,7 +39,8 @@ enum {
     FQB_E_ARG = 50,      /* bad argument (null pointer, misaligned buffer, ...) */
     FQB_E_STATE = 51,    /* call out of order (e.g. submit without acquire) */
     FQB_E_NOMEM = 52,
-    FQB_E_CUDA = 100     /* CUDA runtime failure; fqb_last_error() has the text */
+    FQB_E_CUDA = 100,    /* CUDA runtime failure; fqb_last_error() has the text */
+    FQB_E_NCCL = 101     /* NCCL missing or failing (multi-rank entry points only); fqb_last_error() */
 };
 
 /* The reference refuses records that do not fit its 68 KiB window (src/lib.rs:129,278-283).  Whether a
@@ -217,6 +218,38 @@ int fqb_stream_acquire(fqb_ctx *ctx, uint8_t **pinned, uint64_t *cap);
 int fqb_stream_submit(fqb_ctx *ctx, uint64_t n_valid);
 /* end of input: drains the ring, returns outcome + stats */
 int fqb_stream_finish(fqb_ctx *ctx, fqb_result *res, uint64_t *host_stats);
+
+/* ---- N ranks, one byte shard per GPU: the one collective of the path ---------------------------
+ * The reference has nothing to shard (parallel_each delimits on ONE thread, src/lib.rs:535); this is the
+ * B200-side answer to "the byte stream shards by chunk across the GPUs of one box" (SURVEY.md 8(e)).
+ * One process per GPU.  Every rank parses its shard at once (fqb_parse_device with FQB_F_INFER_START for all
+ * shards but the first), then ONE all-reduce(sum, u64) over NVLink combines
+ *     [ statistics block | world x 8 outcome words ]
+ * -- every rank has written its outcome (the words of fqb_device_result) into its own slot and zeros into the
+ * others, so the sum of the slots is the gather of the outcomes.  Every rank then holds the global statistics
+ * and all outcomes: exact line numbers = prefix of the n_lines, first error in stream order, and whether every
+ * inferred shard start was right (line_phase == prefix & 3) -- if not, the caller parses those shards again
+ * with the exact line_base and reduces once more (never observed on well-formed input).
+ * NCCL is bound at run time (dlopen of libnccl.so.2): none is needed for world == 1. */
+#define FQB_MAX_WORLD 64
+#define FQB_COMM_ID_BYTES 128
+/* rank 0: a fresh ncclUniqueId, to be handed to the other ranks by whatever the caller has (a file, MPI, ...) */
+int fqb_comm_unique_id(uint8_t out[FQB_COMM_ID_BYTES]);
+/* collective over all ranks (ncclCommInitRank); world == 1 needs no id and no NCCL */
+int fqb_comm_init(fqb_ctx *ctx, int rank, int world, const uint8_t id[FQB_COMM_ID_BYTES]);
+int fqb_comm_destroy(fqb_ctx *ctx);
+int fqb_comm_rank(fqb_ctx *ctx);
+int fqb_comm_world(fqb_ctx *ctx);
+/* enqueue the all-reduce of the last parse's [block | slots] on `stream` (after the parse, stream order) */
+int fqb_allreduce(fqb_ctx *ctx, void *stream);
+/* wait for it; host_stats (fqb_stats_words(P) words, may be NULL) = the global block, outcomes
+ * (8 x world words, may be NULL) = per rank: status, finished, n_records, n_lines, err_offset, tail_offset,
+ * line_phase, 0.  One device-to-host copy, one synchronisation. */
+int fqb_fetch_reduced(fqb_ctx *ctx, void *stream, uint64_t *host_stats, uint64_t *outcomes);
+/* the send buffer itself -- fqb_exchange_words(ctx) = fqb_stats_words(P) + 8 * world device-resident words --
+ * for callers that run the collective with their own library */
+uint64_t *fqb_device_exchange(fqb_ctx *ctx);
+size_t fqb_exchange_words(fqb_ctx *ctx);
 
 /* ---- pinned host memory helpers ------------------------------------------------------- */
 int fqb_host_alloc(uint64_t bytes, void **out); /* cudaHostAlloc */

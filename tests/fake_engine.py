@@ -26,9 +26,19 @@ class FakeEngine:
         self.lie_phase = lie_phase      # report a wrong inferred phase (the driver must parse again)
         self.fail_infer = fail_infer    # answer E_PHASE to every inference
         self.n_parses = 0
-        self._stats = torch.zeros(8 + max_len + 2 + 6 * max_len + 256 * max_len, dtype=torch.int64)
+        self._nw = 8 + max_len + 2 + 6 * max_len + 256 * max_len
         self._out = None
         self._res = torch.zeros(8, dtype=torch.int64)
+        self.set_rank(0, 1)
+
+    def set_rank(self, rank, world):
+        """the send buffer of the one collective: [statistics block | world x 8 outcome words] (fqb_device_exchange)"""
+        self.rank, self.world = rank, world
+        self._x = torch.zeros(self._nw + 8 * world, dtype=torch.int64)
+        self._stats = self._x[:self._nw]
+
+    def device_exchange(self):
+        return self._x
 
     def device_result(self):
         """the 8-word outcome block of fqb_device_result"""
@@ -38,6 +48,8 @@ class FakeEngine:
         self._out = o
         self._res[:] = torch.tensor([o.status, int(o.finished), o.n_records, o.n_lines, o.err_offset,
                                      -1 if o.tail_offset is None else o.tail_offset, o.line_phase, 0], dtype=torch.int64)
+        self._x[self._nw:] = 0
+        self._x[self._nw + 8 * self.rank: self._nw + 8 * self.rank + 8] = self._res
 
     def count_lines(self, view, n):
         return int((view[:n].numpy() == 10).sum())

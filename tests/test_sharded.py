@@ -29,7 +29,7 @@ def _worker(rank, world, init_file, data_bytes, mode, q):
     eng = FakeEngine(150, lie_phase=(mode == "lie" and rank == 1), fail_infer=(mode == "nophase"))
     sp = ShardedParser(eng, dist=dist)
     out, st = sp.parse(ShardSpec(t, a, b, halo, front, is_last=(b + halo == total)))
-    q.put((rank, out, st.words.copy(), eng.n_parses, sp.reparsed))
+    q.put((rank, out, st.words.copy(), eng.n_parses, (sp.reparsed, sp.collectives)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,6 +70,8 @@ def test_two_ranks_match_single_stream(mode, tmp_path):
             assert n_parses == (1 if mode == "plain" else 2), (mode, n_parses)
         else:
             assert n_parses == 1
+        # the common case is ONE collective: the all-reduce of [block | outcome slots] is also the gather
+        assert reparsed[1] == 1 if mode == "plain" else reparsed[1] > 1
 
 
 def test_error_in_first_shard_silences_the_second(tmp_path):
