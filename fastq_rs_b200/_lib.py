@@ -15,7 +15,7 @@ ABI_VERSION = int(os.environ.get("FQB_ABI", "3"))   # (FQB_ABI: A/B runs against
 
 # status codes (include/fastq_b200.h)
 OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
-E_ARG, E_STATE, E_NOMEM, E_CUDA, E_NCCL = 50, 51, 52, 100, 101
+E_ARG, E_STATE, E_NOMEM, E_CANCELLED, E_CUDA, E_NCCL = 50, 51, 52, 53, 100, 101
 MAX_WORLD, COMM_ID_BYTES = 64, 128
 KEEP_ALL, KEEP_DNA, KEEP_DNAN = 0, 1, 2
 F_HIST, F_INDEX, F_LINE_START, F_EOF, F_FRONT16, F_INFER_START, F_PARTIAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
@@ -34,6 +34,7 @@ SYMBOLS = [
     "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter", "fqb_last_path",
     "fqb_comm_unique_id", "fqb_comm_init", "fqb_comm_destroy", "fqb_comm_rank", "fqb_comm_world", "fqb_allreduce",
     "fqb_fetch_reduced", "fqb_device_exchange", "fqb_exchange_words",
+    "fqb_batch_begin", "fqb_batch_close", "fqb_next_batch", "fqb_release_batch", "fqb_batch_cancel", "fqb_batch_end",
 ]
 
 
@@ -53,6 +54,12 @@ class Result(C.Structure):
     _fields_ = [("status", C.c_int32), ("finished", C.c_int32), ("n_records", C.c_uint64),
                 ("n_lines", C.c_uint64), ("err_offset", C.c_uint64), ("tail_offset", C.c_uint64),
                 ("line_phase", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("n_avail", C.c_uint64), ("stream_offset", C.c_uint64),
+                ("line_ends", C.c_void_p), ("n_records", C.c_uint64), ("first_record", C.c_uint64),
+                ("err_offset", C.c_uint64), ("token", C.c_uint64), ("status", C.c_int32), ("last", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -133,6 +140,18 @@ def lib():
     L.fqb_synth_var_sizes_device.restype = i32
     L.fqb_last_path.argtypes = [vp, C.POINTER(u64 * 3)]
     L.fqb_last_path.restype = i32
+    L.fqb_batch_begin.argtypes = [vp, u32]
+    L.fqb_batch_begin.restype = i32
+    L.fqb_batch_close.argtypes = [vp]
+    L.fqb_batch_close.restype = i32
+    L.fqb_next_batch.argtypes = [vp, C.POINTER(Batch)]
+    L.fqb_next_batch.restype = i32
+    L.fqb_release_batch.argtypes = [vp, u64]
+    L.fqb_release_batch.restype = i32
+    L.fqb_batch_cancel.argtypes = [vp]
+    L.fqb_batch_cancel.restype = i32
+    L.fqb_batch_end.argtypes = [vp, C.POINTER(Result)]
+    L.fqb_batch_end.restype = i32
     L.fqb_comm_unique_id.argtypes = [vp]
     L.fqb_comm_unique_id.restype = i32
     L.fqb_comm_init.argtypes = [vp, i32, i32, vp]

@@ -11,6 +11,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +99,28 @@ __global__ void __launch_bounds__(256) fq_index_out_kernel(const uint32_t* __res
         out[off + i] = idx[i];
 }
 
+// batch mode: the outcome of ONE chunk and its line ends, written by the device into pinned host memory right
+// behind the chunk's kernels (stream order) -- the consumer thread waits for an event, not for the stream
+constexpr int BATCH_INFO_WORDS = 8;   // status, n_records, n_lines, err_offset, line_base before the chunk, tail + 1, -, -
+__global__ void __launch_bounds__(256) fq_batch_out_kernel(const uint32_t* __restrict__ idx, const DevResult* r,
+                                                           unsigned long long* info, uint32_t* out, unsigned long long cap)
+{
+    const unsigned long long n = r->n_lines;
+    const unsigned long long m = n < cap ? n : cap;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) out[i] = idx[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        info[0] = (unsigned long long)r->status;
+        info[1] = r->n_records;
+        info[2] = n;
+        info[3] = r->err_offset;
+        info[4] = r->line_end - n;
+        info[5] = r->tail_start == NONE64 ? 0ull : r->tail_start + 1ull;
+        info[6] = 0;
+        info[7] = 0;
+    }
+}
+
 struct Slot {  // one stage of the streaming ring
     uint8_t* h_pinned = nullptr;
     cudaEvent_t copied = nullptr;  // H2D of the chunk in this host slot finished
@@ -169,6 +193,32 @@ struct fqb_ctx {
     uint64_t pending_bytes = 0, pending_chunk = 0, pending_off = 0;
     bool pending_line_start = true;  // the byte before the pending chunk is '\n' (or stream start)
     bool last_byte_nl = true;        // last byte copied so far is '\n' (true before the first byte)
+    uint8_t* h_ring = nullptr;   // n_slots pinned slots back to back + MAXREC mirror of slot 0
+    // batch mode (fqb_batch_begin .. fqb_next_batch): one producer thread (acquire / submit / close), one
+    // consumer thread (next / release); everything below is guarded by `mu`
+    struct BChunk {
+        uint64_t no = ~0ull;         // chunk number held by this host slot
+        uint64_t off = 0, n_bytes = 0;
+        bool line_start = false;     // the byte in front of the chunk is '\n' (or the stream starts here)
+        bool launched = false;       // its parse has been enqueued (event `parsed` recorded)
+        bool released = true;        // the consumer has given the batch back
+        cudaEvent_t parsed = nullptr;
+        unsigned long long* h_info = nullptr;   // pinned, written by the device: BATCH_INFO_WORDS words
+        uint32_t* h_index = nullptr;            // pinned: the chunk's line ends
+        uint32_t* h_index_dev = nullptr;        // its device alias
+        unsigned long long* h_info_dev = nullptr;
+        size_t index_cap = 0;
+        const uint32_t* d_index = nullptr;      // device copy (valid until the device slot is reused)
+    };
+    std::vector<BChunk> bchunks;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool batch_mode = false, batch_closed = false, batch_cancel = false, batch_failed = false;
+    uint64_t b_total = ~0ull;        // chunks of the stream (known once the producer has closed it)
+    uint64_t b_next = 0;             // next chunk to deliver
+    uint64_t b_held = 0;             // batches delivered and not yet released
+    uint64_t b_records = 0;          // records delivered so far
+    int b_status = 0;                // status that ended the stream
     // host index collection (generic closure path)
     uint32_t* host_index = nullptr;
     uint32_t* host_index_dev = nullptr;   // device alias of host_index when the caller's buffer is pinned
@@ -233,7 +283,7 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     ctx->nwords = stats_words(ctx->P);
     ctx->slot_bytes = cfg->slot_bytes ? (cfg->slot_bytes + 4095) / 4096 * 4096 : (64ull << 20);
     if (ctx->slot_bytes < 2 * (uint64_t)MAXREC) ctx->slot_bytes = 2 * (uint64_t)MAXREC;
-    ctx->n_slots = cfg->n_slots ? cfg->n_slots : 3;
+    ctx->n_slots = cfg->n_slots ? cfg->n_slots : 4;
     if (ctx->n_slots < 2) ctx->n_slots = 2;
     cudaError_t e;
 #define CKC(call)                        \
@@ -277,11 +327,17 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
 
 static void stream_free(fqb_ctx* ctx)
 {
-    for (auto& s : ctx->slots) {
-        if (s.h_pinned) cudaFreeHost(s.h_pinned);
+    for (auto& s : ctx->slots)
         if (s.copied) cudaEventDestroy(s.copied);
-    }
     ctx->slots.clear();
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    ctx->h_ring = nullptr;
+    for (auto& b : ctx->bchunks) {
+        if (b.parsed) cudaEventDestroy(b.parsed);
+        if (b.h_info) cudaFreeHost(b.h_info);
+        if (b.h_index) cudaFreeHost(b.h_index);
+    }
+    ctx->bchunks.clear();
     for (auto& d : ctx->dslots) {
         if (d.done) cudaEventDestroy(d.done);
         if (d.d_index) cudaFree(d.d_index);
@@ -654,10 +710,14 @@ static int stream_alloc(fqb_ctx* ctx)
     CK(cudaMalloc(&ctx->d_total, ctx->nwords * 8));
     CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    // the pinned host slots lie back to back like the device slots, with MAXREC bytes behind the last one that
+    // mirror the head of slot 0: a record that starts in one slot and ends in the next is contiguous in host
+    // memory too (batch mode hands out records that borrow the ring, fqb_next_batch)
+    CK(cudaHostAlloc(&ctx->h_ring, (size_t)ctx->n_slots * ctx->slot_bytes + MAXREC + 64, cudaHostAllocDefault));
     ctx->slots.resize(ctx->n_slots);
-    for (auto& s : ctx->slots) {
-        CK(cudaHostAlloc(&s.h_pinned, ctx->slot_bytes, cudaHostAllocDefault));
-        CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    for (uint32_t k = 0; k < ctx->n_slots; ++k) {
+        ctx->slots[k].h_pinned = ctx->h_ring + (size_t)k * ctx->slot_bytes;
+        CK(cudaEventCreateWithFlags(&ctx->slots[k].copied, cudaEventDisableTiming));
     }
     ctx->dslots.resize(ctx->n_dev);
     for (auto& d : ctx->dslots) CK(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
@@ -708,7 +768,22 @@ static int launch_pending(fqb_ctx* ctx, uint64_t next_bytes, bool eof)
     }
     int rc = enqueue_parse(ctx, &sh, ctx->s_comp, ctx->d_carry, ctx->d_total, false);
     if (rc) return rc;
-    if ((ctx->stream_flags & FQB_F_INDEX) && ctx->host_index_dev) {
+    if (ctx->batch_mode) {
+        // batch mode: outcome + line ends of this chunk into the pinned buffers of its host slot, then the event the
+        // consumer waits for
+        fqb_ctx::BChunk& bc = ctx->bchunks[i % ctx->n_slots];
+        fq_batch_out_kernel<<<ctx->num_sms * 2, 256, 0, ctx->s_comp>>>(sh.d_index, ctx->d_res, bc.h_info_dev, bc.h_index_dev,
+                                                                       bc.index_cap);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+        CK(cudaEventRecord(bc.parsed, ctx->s_comp));
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            bc.d_index = sh.d_index;
+            bc.launched = true;
+        }
+        ctx->cv.notify_all();
+    } else if ((ctx->stream_flags & FQB_F_INDEX) && ctx->host_index_dev) {
         // generic-closure path, pinned index buffer: written by the device, in stream order
         fq_index_out_kernel<<<ctx->num_sms * 2, 256, 0, ctx->s_comp>>>(sh.d_index, ctx->d_res, ctx->d_carry,
                                                                        ctx->host_index_dev, ctx->host_index_cap);
@@ -757,6 +832,19 @@ static int submit_chunk(fqb_ctx* ctx, const uint8_t* h_src, uint64_t n, cudaEven
         int rc = launch_pending(ctx, n, n < ctx->slot_bytes);
         if (rc) return rc;
     }
+    if (ctx->batch_mode) {
+        fqb_ctx::BChunk& bc = ctx->bchunks[i % ctx->n_slots];
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        bc.no = i;
+        bc.off = ctx->stream_pos;
+        bc.n_bytes = n;
+        bc.line_start = ctx->last_byte_nl;
+        bc.launched = false;
+        bc.released = false;
+        // the head of slot 0 again behind the last slot: the last record of the chunk before it reads on there
+        if (i % ctx->n_slots == 0 && i > 0)
+            memcpy(ctx->h_ring + (size_t)ctx->n_slots * ctx->slot_bytes, ctx->h_ring, (size_t)std::min<uint64_t>(n, MAXREC));
+    }
     ctx->have_pending = true;
     ctx->pending_line_start = ctx->last_byte_nl;
     ctx->last_byte_nl = h_src[n - 1] == '\n';
@@ -776,6 +864,16 @@ int fqb_stream_acquire(fqb_ctx* ctx, uint8_t** pinned, uint64_t* cap)
     if (ctx->fill == 0 && s.copied_pending) {
         CK(cudaEventSynchronize(s.copied));  // empty_recv.recv(): wait until the slot has been drained
         s.copied_pending = false;
+    }
+    if (ctx->batch_mode && ctx->fill == 0) {
+        // the slot still backs the batch of the chunk it held before: that batch must have been given back
+        // (fqb_release_batch).  The batch of the chunk in front of THAT one reads its last record on into this
+        // slot (or into the mirror of slot 0); it was given back before the slot in front of this one was refilled --
+        // slots are filled in order -- so this one condition covers it.
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        const uint32_t k = (uint32_t)(ctx->chunk_no % ctx->n_slots);
+        ctx->cv.wait(lk, [&] { return ctx->batch_cancel || ctx->bchunks[k].released; });
+        if (ctx->batch_cancel) return FQB_E_CANCELLED;
     }
     *pinned = s.h_pinned + ctx->fill;
     *cap = ctx->slot_bytes - ctx->fill;
@@ -905,6 +1003,235 @@ int fqb_parse_host(fqb_ctx* ctx, const uint8_t* bytes, uint64_t n, uint64_t stre
     return rc;
 }
 
+
+// ==========================================================================================
+// batch mode: the generic-closure path, asynchronous (RecordSet hand-off, src/lib.rs:306-426, 509-566)
+// ==========================================================================================
+// Producer thread:  fqb_batch_begin, then fqb_stream_acquire / fqb_stream_submit per read() as in the streaming
+//                   ring (thread_reader's protocol), fqb_batch_close at the end of the input.
+// Consumer thread:  fqb_next_batch hands out, chunk by chunk, the records the GPU has delimited -- bytes borrowed
+//                   from the pinned ring + their line ends -- while the producer keeps reading and the GPU keeps
+//                   delimiting the chunks behind; fqb_release_batch gives the memory back (RecordSet dropped).
+// A batch holds the records that START in its chunk; the last of them may end in the next chunk (contiguous in the
+// host ring), and its last line ends then come from that chunk's index -- which is why batch i is handed out once
+// chunk i + 1 has been delimited as well (or the input has ended).
+
+static int batch_alloc(fqb_ctx* ctx)
+{
+    if (!ctx->bchunks.empty()) return FQB_OK;
+    ctx->bchunks.resize(ctx->n_slots);
+    for (auto& b : ctx->bchunks) {
+        CK(cudaEventCreateWithFlags(&b.parsed, cudaEventDisableTiming));
+        CK(cudaHostAlloc(&b.h_info, BATCH_INFO_WORDS * 8, cudaHostAllocMapped));
+        b.index_cap = (size_t)(ctx->slot_bytes / 8) + 64;       // lines of >= 8 bytes on average; grown on demand
+        CK(cudaHostAlloc(&b.h_index, b.index_cap * 4, cudaHostAllocMapped));
+        void* d = nullptr;
+        CK(cudaHostGetDevicePointer(&d, b.h_info, 0));
+        b.h_info_dev = static_cast<unsigned long long*>(d);
+        CK(cudaHostGetDevicePointer(&d, b.h_index, 0));
+        b.h_index_dev = static_cast<uint32_t*>(d);
+    }
+    return FQB_OK;
+}
+
+int fqb_batch_begin(fqb_ctx* ctx, uint32_t flags)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (ctx->streaming || ctx->batch_mode) return FQB_E_STATE;
+    if (ctx->n_slots < 4) {
+        ctx->err = "batch mode needs fqb_config.n_slots >= 4";
+        return FQB_E_STATE;
+    }
+    int rc = fqb_stream_begin(ctx, (flags & FQB_F_HIST) | FQB_F_INDEX);
+    if (rc) return rc;
+    rc = batch_alloc(ctx);
+    if (rc) {
+        ctx->streaming = false;
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& b : ctx->bchunks) {
+        b.no = ~0ull;
+        b.launched = false;
+        b.released = true;
+    }
+    ctx->batch_mode = true;
+    ctx->batch_closed = ctx->batch_cancel = ctx->batch_failed = false;
+    ctx->b_total = ~0ull;
+    ctx->b_next = ctx->b_held = ctx->b_records = 0;
+    ctx->b_status = 0;
+    return FQB_OK;
+}
+
+int fqb_batch_close(fqb_ctx* ctx)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (!ctx->batch_mode || ctx->acquired || ctx->batch_closed) return FQB_E_STATE;
+    int rc = FQB_OK;
+    if (ctx->fill) {   // partially filled last slot
+        Slot& s = ctx->slots[ctx->chunk_no % ctx->n_slots];
+        rc = submit_chunk(ctx, s.h_pinned, ctx->fill, s.copied);
+        s.copied_pending = true;
+        ctx->fill = 0;
+    }
+    if (rc == FQB_OK && ctx->have_pending) rc = launch_pending(ctx, 0, true);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->b_total = ctx->chunk_no;
+        ctx->batch_closed = true;
+        if (rc != FQB_OK) ctx->batch_failed = true;
+    }
+    ctx->cv.notify_all();
+    return rc;
+}
+
+int fqb_next_batch(fqb_ctx* ctx, fqb_batch* out)
+{
+    if (!ctx || !out) return FQB_E_ARG;
+    if (!ctx->batch_mode) return FQB_E_STATE;
+    memset(out, 0, sizeof *out);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    if (ctx->b_status != 0) return FQB_E_STATE;                       // the stream has ended with an error batch
+    if (ctx->b_held + 3 > ctx->n_slots) {
+        ctx->err = "fqb_next_batch: release a batch first (at most n_slots - 3 may be held)";
+        return FQB_E_STATE;
+    }
+    const uint64_t i = ctx->b_next;
+    // chunk i delimited, and chunk i + 1 too unless chunk i is the last one
+    auto ready = [&](uint64_t c) { return ctx->bchunks[c % ctx->n_slots].no == c && ctx->bchunks[c % ctx->n_slots].launched; };
+    ctx->cv.wait(lk, [&] {
+        if (ctx->batch_cancel || ctx->batch_failed) return true;
+        if (ctx->batch_closed && i >= ctx->b_total) return true;
+        if (!ready(i)) return false;
+        return ready(i + 1) || (ctx->batch_closed && i + 1 >= ctx->b_total);
+    });
+    if (ctx->batch_cancel) return FQB_E_CANCELLED;
+    if (ctx->batch_failed) return FQB_E_CUDA;
+    if (i >= ctx->b_total) {                                          // an empty stream, or everything handed out
+        out->last = 1;
+        out->first_record = ctx->b_records;
+        out->token = UINT64_MAX;                                      // nothing to release
+        return FQB_OK;
+    }
+    fqb_ctx::BChunk& bc = ctx->bchunks[i % ctx->n_slots];
+    const bool have_next = i + 1 < ctx->b_total;
+    fqb_ctx::BChunk* bn = have_next ? &ctx->bchunks[(i + 1) % ctx->n_slots] : nullptr;
+    lk.unlock();
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(bc.parsed));
+    if (bn) CK(cudaEventSynchronize(bn->parsed));
+    const unsigned long long status = bc.h_info[0], n_rec = bc.h_info[1], n_lines = bc.h_info[2], lb = bc.h_info[4];
+    // the chunk has more line ends than its pinned index holds: fetch them from the device copy (still valid: the
+    // device slot is reused only after this batch has been handed out) into a larger buffer
+    if (n_lines + 8 > bc.index_cap) {
+        uint32_t* bigger = nullptr;
+        const size_t cap = (size_t)n_lines + 64;
+        CK(cudaHostAlloc(&bigger, cap * 4, cudaHostAllocMapped));
+        CK(cudaMemcpy(bigger, bc.d_index, (size_t)n_lines * 4, cudaMemcpyDeviceToHost));
+        cudaFreeHost(bc.h_index);
+        bc.h_index = bigger;
+        bc.index_cap = cap;
+        void* d = nullptr;
+        CK(cudaHostGetDevicePointer(&d, bigger, 0));
+        bc.h_index_dev = static_cast<uint32_t*>(d);
+    }
+    // line ends in front of the first record that starts in the chunk (they end a record of the chunk before)
+    const uint64_t lead = (bc.line_start && (lb & 3) == 0) ? 0 : 4 - (lb & 3);
+    const uint64_t need = 4 * n_rec;
+    uint64_t have = n_lines > lead ? n_lines - lead : 0;
+    if (have < need) {
+        // the last record ends in the next chunk: its remaining line ends lead that chunk's index
+        if (!bn) return FQB_E_STATE;
+        const uint64_t miss = need - have;
+        if (miss > 4 || bn->h_info[2] < miss || bc.index_cap < lead + need) return FQB_E_STATE;
+        for (uint64_t k = 0; k < miss; ++k) bc.h_index[lead + have + k] = bn->h_index[k];
+        have = need;
+    }
+    // where the first record starts: right behind the `lead`-th line end of the chunk (or at its first byte)
+    uint64_t first_off = bc.off;
+    if (lead) {
+        if (n_lines < lead) {
+            first_off = bc.off + bc.n_bytes;                          // no record starts in this chunk
+        } else {
+            const uint32_t e = bc.h_index[lead - 1];
+            first_off = bc.off + (uint32_t)(e - (uint32_t)bc.off) + 1;
+        }
+    }
+    uint64_t end_off = first_off;
+    if (n_rec) {
+        const uint32_t e = bc.h_index[lead + need - 1];
+        end_off = first_off + (uint32_t)(e - (uint32_t)first_off) + 1;
+    }
+    out->bytes = ctx->h_ring + (size_t)(i % ctx->n_slots) * ctx->slot_bytes + (first_off - bc.off);
+    out->n_bytes = end_off - first_off;
+    out->n_avail = bc.off + bc.n_bytes + (bn ? std::min<uint64_t>(bn->n_bytes, MAXREC) : 0) - first_off;
+    out->stream_offset = first_off;
+    out->line_ends = bc.h_index + lead;
+    out->n_records = n_rec;
+    out->status = (int32_t)status;
+    out->err_offset = bc.h_info[3];
+    out->token = i;
+    lk.lock();
+    out->first_record = ctx->b_records;
+    ctx->b_records += n_rec;
+    ctx->b_next = i + 1;
+    ctx->b_held += 1;
+    if (status != 0) ctx->b_status = (int)status;
+    out->last = (status != 0 || (ctx->batch_closed && i + 1 >= ctx->b_total)) ? 1 : 0;
+    return FQB_OK;
+}
+
+int fqb_release_batch(fqb_ctx* ctx, uint64_t token)
+{
+    if (!ctx) return FQB_E_ARG;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        fqb_ctx::BChunk& bc = ctx->bchunks[token % ctx->n_slots];
+        if (!ctx->batch_mode || bc.no != token || bc.released) return FQB_E_STATE;
+        bc.released = true;
+        ctx->b_held -= 1;
+    }
+    ctx->cv.notify_all();
+    return FQB_OK;
+}
+
+int fqb_batch_cancel(fqb_ctx* ctx)
+{
+    if (!ctx) return FQB_E_ARG;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->batch_cancel = true;
+    }
+    ctx->cv.notify_all();
+    return FQB_OK;
+}
+
+int fqb_batch_end(fqb_ctx* ctx, fqb_result* res)
+{
+    if (!ctx) return FQB_E_ARG;
+    if (!ctx->batch_mode) return FQB_E_STATE;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->s_copy);
+    cudaStreamSynchronize(ctx->s_comp);
+    if (res) {
+        memset(res, 0, sizeof *res);
+        if (cudaMemcpy(ctx->h_carry, ctx->d_carry, sizeof(DevCarry), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            res->status = ctx->h_carry->status;
+            res->finished = ctx->h_carry->status == 0 && ctx->batch_closed && !ctx->batch_cancel;
+            res->n_records = ctx->h_carry->n_records;
+            res->n_lines = ctx->h_carry->n_lines;
+            res->err_offset = ctx->h_carry->err_offset;
+            res->tail_offset = UINT64_MAX;
+        }
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->batch_mode = false;
+    ctx->streaming = false;
+    ctx->acquired = false;
+    ctx->fill = 0;
+    ctx->have_pending = false;
+    return FQB_OK;
+}
 
 // ==========================================================================================
 // N ranks, one byte shard each: the ONE collective of the path behind the ABI

@@ -293,6 +293,56 @@ class Engine:
                "fqb_stream_finish")
         return self._outcome(res), (Stats(self.max_len, words) if want_stats else None)
 
+    # ---- batch mode: the generic-closure path, asynchronous ------------------------------------
+    def batch_begin(self, hist: bool = False) -> bool:
+        """False if the context is busy with another stream (one ring per context) or has too few slots"""
+        rc = self.L.fqb_batch_begin(self.ctx, F_HIST if hist else 0)
+        if rc == _lib.E_STATE:
+            return False
+        _check(self.ctx, rc, "fqb_batch_begin")
+        return True
+
+    def batch_acquire(self):
+        """producer: the next pinned slot (None once the consumer has cancelled)"""
+        p, cap = C.c_void_p(), C.c_uint64()
+        rc = self.L.fqb_stream_acquire(self.ctx, C.byref(p), C.byref(cap))
+        if rc == _lib.E_CANCELLED:
+            return None
+        _check(self.ctx, rc, "fqb_stream_acquire")
+        return (C.c_uint8 * cap.value).from_address(p.value)
+
+    def batch_close(self):
+        _check(self.ctx, self.L.fqb_batch_close(self.ctx), "fqb_batch_close")
+
+    def next_batch(self):
+        """consumer: (data: uint8 view of the pinned bytes -- the records, then whatever of the stream follows them in
+        the ring --, ends: int64 [n, 4] offsets of the line ends within data, status, err_offset, stream_offset,
+        first_record, last, token) -- valid until release_batch(token)"""
+        b = _lib.Batch()
+        rc = self.L.fqb_next_batch(self.ctx, C.byref(b))
+        if rc == _lib.E_CANCELLED:
+            return None
+        _check(self.ctx, rc, "fqb_next_batch")
+        n = int(b.n_records)
+        data = np.ctypeslib.as_array((C.c_uint8 * int(b.n_avail)).from_address(b.bytes)) if b.n_avail else np.empty(0, np.uint8)
+        if n:
+            raw = np.ctypeslib.as_array((C.c_uint32 * (4 * n)).from_address(b.line_ends))
+            ends = (raw - np.uint32(b.stream_offset & 0xFFFFFFFF)).astype(np.uint32).astype(np.int64).reshape(n, 4)
+        else:
+            ends = np.empty((0, 4), dtype=np.int64)
+        return data, ends, int(b.status), int(b.err_offset), int(b.stream_offset), int(b.first_record), bool(b.last), int(b.token)
+
+    def release_batch(self, token: int):
+        _check(self.ctx, self.L.fqb_release_batch(self.ctx, token), "fqb_release_batch")
+
+    def batch_cancel(self):
+        self.L.fqb_batch_cancel(self.ctx)
+
+    def batch_end(self) -> Outcome:
+        res = _lib.Result()
+        _check(self.ctx, self.L.fqb_batch_end(self.ctx, C.byref(res)), "fqb_batch_end")
+        return self._outcome(res)
+
     # ---- synthetic data (bench / tests) ----------------------------------------------------
     def synth_fixed(self, out, n: int, byte_off: int = 0, read_len: int = 150,
                     seed: int = _lib.SYNTH_SEED, stream=None):

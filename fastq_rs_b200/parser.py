@@ -35,10 +35,12 @@ CHUNK_BYTES = 32 << 20  # refill size of the generic-closure path (the reference
 _default_engines: dict = {}
 
 
-def default_engine(max_len: int = 150, device: int = 0) -> Engine:
-    key = (max_len, device)
+def default_engine(max_len: int = 150, device: int = 0, k: int = 0) -> Engine:
+    """the k-th shared engine for (max_len, device): a context serves one stream at a time, so parsers that run
+    side by side (each_zipped) each take their own"""
+    key = (max_len, device, k)
     if key not in _default_engines:
-        _default_engines[key] = Engine(max_len=max_len, device=device, slot_bytes=8 << 20)
+        _default_engines[key] = Engine(max_len=max_len, device=device, slot_bytes=8 << 20, n_slots=4)
     return _default_engines[key]
 
 
@@ -130,6 +132,49 @@ class RecordSet:  # src/lib.rs:306-336
         return len(self._starts) == 0
 
 
+def _next_fill(fill_end: int, cur: int) -> int:
+    """Buffer::replace_buffer + read_into (src/buffer.rs:30-48,74-100) in stream coordinates: the n = fill_end - cur
+    leftover bytes are parked so that they end at ceil16(n); the read asks for n_free rounded down to 4096 (all of
+    n_free below 4096).  Returns the new fill end (== fill_end when the buffer is full: "record too long")."""
+    n = fill_end - cur
+    new_end = (n + 15) & ~15
+    free = BUFSIZE - new_end
+    return fill_end + (free if free < 4096 else free - free % 4096)
+
+
+def _owned_set(pend: list) -> "RecordSet":
+    """a RecordSet that owns a copy of its records' bytes (src/lib.rs:308-311)"""
+    if not pend:
+        return RecordSet(memoryview(b""), np.empty(0, np.int64), np.empty((0, 4), np.int64))
+    buf = b"".join(p[0] for p in pend)
+    starts = np.empty(len(pend), np.int64)
+    ends = np.empty((len(pend), 4), np.int64)
+    at = 0
+    for k, (raw, s_abs, e4) in enumerate(pend):
+        starts[k] = at
+        ends[k] = np.asarray(e4, dtype=np.int64) - s_abs + at
+        at += len(raw)
+    return RecordSet(memoryview(buf), starts, ends)
+
+
+def _detect_point(d: "_Delimited", status: int, e: int):
+    """Stream offset of the byte whose presence in the buffer makes from_buffer return the error `status` for the
+    record at stream offset e (src/records.rs:201-247): '@' -> e itself; '+' -> the byte behind the sequence line;
+    length mismatch -> the fourth line end.  None if the host's copy of the stream does not reach that far."""
+    if status == 1:
+        return e
+    buf = d.buf
+    rel = e - d.base
+    pos = rel
+    need = 2 if status == 2 else 4
+    for k in range(need):
+        nxt = bytes(buf[pos:pos + 70000]).find(b"\n")
+        if nxt < 0:
+            return None
+        pos += nxt + 1
+    return d.base + (pos if status == 2 else pos - 1)
+
+
 def _make_record(buf: memoryview, start: int, ends) -> RefRecord:
     e0, e1, e2, e3 = (int(x) for x in ends)
     return RefRecord(buf[start:e3 + 1], e0 - start, e1 - start, e2 - start, e3 - start, start)
@@ -168,13 +213,15 @@ def _fill(reader, view: np.ndarray) -> int:
 
 
 class _Delimited:
-    """Result of the GPU delimiting pass over one refill of the stream: record starts and line ends
-    (relative to `data`); `base` = stream offset of data[0], `delivered` = records of earlier refills."""
+    """Result of the GPU delimiting pass over one refill / one batch of the stream: record starts and line ends
+    (relative to `data`); `base` = stream offset of data[0], `delivered` = records of earlier refills.  `data`
+    may reach beyond the last delivered record (the bad or incomplete record that follows it)."""
 
-    def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray, base: int = 0, delivered: int = 0):
-        self.base, self.delivered = base, delivered
+    def __init__(self, data: np.ndarray, outcome: Outcome, index: np.ndarray, base: int = 0, delivered: int = 0,
+                 rel_ends: Optional[np.ndarray] = None, at_eof: bool = False):
+        self.base, self.delivered, self.at_eof = base, delivered, at_eof
         n = outcome.n_records
-        ends = index[:4 * n].astype(np.int64).reshape(n, 4) - base     # relative to data[0]
+        ends = rel_ends if rel_ends is not None else index[:4 * n].astype(np.int64).reshape(n, 4) - base   # relative to data[0]
         starts = np.empty(n, dtype=np.int64)
         if n:
             starts[0] = 0
@@ -250,16 +297,27 @@ class RecordRefIter:  # src/lib.rs:241-304
     def get(self) -> Optional[RefRecord]:
         return self._cur
 
+    def close(self) -> None:
+        """drop the parser: stops the reader thread of the batch mode, gives the ring back"""
+        self._done = True
+        close = getattr(self._chunks, "close", None)
+        if close is not None:
+            close()
+
 
 class Parser:
     """Parser::new(reader) (src/lib.rs:200).  `reader`: bytes-like, uint8 ndarray, or an object
     with .read().  `max_len` = positions tracked by stats()."""
 
     def __init__(self, reader, engine: Optional[Engine] = None, max_len: int = 150,
-                 chunk_bytes: int = CHUNK_BYTES):
+                 chunk_bytes: Optional[int] = None):
+        """`chunk_bytes`: None = readers are consumed through the asynchronous batch mode (ring slots of the
+        engine); a number = synchronous refills of that size (FQB_F_PARTIAL + carry-over)."""
         self._reader = reader
+        self._own_engine = engine is None
+        self._max_len = max_len
         self._engine = engine or default_engine(max_len)
-        self._chunk_bytes = max(1, int(chunk_bytes))
+        self._chunk_bytes = None if chunk_bytes is None else max(1, int(chunk_bytes))
 
     def _chunks(self) -> Iterator[_Delimited]:
         """Delimit the stream refill by refill.  In-memory inputs are one refill; a reader is consumed
@@ -270,11 +328,24 @@ class Parser:
         if isinstance(r, (bytes, bytearray, memoryview, np.ndarray)):
             data = _read_all(r)
             outcome, _, index = eng.parse_host(data, hist=False, want_index=True, want_stats=False)
-            yield _Delimited(data, outcome, index)
+            yield _Delimited(data, outcome, index, at_eof=True)
             return
+        if self._chunk_bytes is None and hasattr(eng, "batch_begin"):
+            k = 0
+            while not eng.batch_begin():
+                # the ring of this context is busy with another parser's stream (each_zipped): take the next of the
+                # shared engines; an engine the caller passed in is the caller's to keep free
+                if not self._own_engine:
+                    raise RuntimeError("the engine is busy with another stream: give every concurrent Parser its own Engine")
+                k += 1
+                eng = self._engine = default_engine(self._max_len, eng.device, k)
+            yield from self._batches()
+            return
+        # (synchronous refills: asked for, or the engine's ring is busy with another stream -- each_zipped over
+        # two parsers that share an engine --, or a stand-in engine without the batch mode)
         left = np.empty(0, dtype=np.uint8)
         base = delivered = 0
-        ch = self._chunk_bytes
+        ch = self._chunk_bytes or CHUNK_BYTES
         while True:
             buf = np.empty(left.size + ch, dtype=np.uint8)
             buf[:left.size] = left
@@ -283,11 +354,67 @@ class Parser:
             buf = buf[:left.size + n]
             outcome, _, index = eng.parse_host(buf, hist=False, want_index=True, want_stats=False,
                                                partial=not eof, stream_offset=base)
-            yield _Delimited(buf, outcome, index, base, delivered)
+            yield _Delimited(buf, outcome, index, base, delivered, at_eof=eof)
             if eof or outcome.status != 0:
                 return
             t = buf.size if outcome.tail_offset is None else outcome.tail_offset - base
             left, base, delivered = buf[t:], base + t, delivered + outcome.n_records
+
+    def _batches(self) -> Iterator[_Delimited]:
+        """The asynchronous form of _chunks (batch mode of the C ABI): a reader thread keeps the pinned ring full
+        (thread_reader's protocol, src/thread_reader.rs:40-50) and the GPU keeps delimiting while this thread hands
+        out the chunks already delimited.  The records of a batch borrow the pinned ring: they are valid until the
+        next batch is asked for -- the lifetime of a RefRecord inside each() (src/lib.rs:248-252)."""
+        eng, r = self._engine, self._reader      # (the caller has begun the batch mode)
+        err: list = []
+
+        def pump():
+            try:
+                while True:
+                    slot = eng.batch_acquire()                   # blocks until a pinned slot is free
+                    if slot is None:
+                        return                                   # the consumer stopped
+                    mv = memoryview(slot).cast("B")
+                    if hasattr(r, "readinto"):
+                        n = r.readinto(mv) or 0
+                    else:
+                        b = r.read(len(mv))
+                        n = len(b)
+                        mv[:n] = b
+                    eng.stream_submit(n)
+                    if not n:
+                        eng.batch_close()
+                        return
+            except BaseException as e:                           # reader errors travel to the caller
+                err.append(e)
+                eng.batch_cancel()
+
+        t = threading.Thread(target=pump, name="reader-thread", daemon=True)
+        t.start()
+        held = None
+        try:
+            while True:
+                if held is not None:
+                    eng.release_batch(held)
+                    held = None
+                nb = eng.next_batch()
+                if nb is None:
+                    break                                        # cancelled: the reader failed
+                data, ends, status, err_off, off, first, last, held = nb
+                if held == 0xFFFFFFFFFFFFFFFF:
+                    held = None                                  # the end-of-input marker borrows nothing
+                outcome = Outcome(status, status == 0, len(ends), 0, err_off, None)
+                yield _Delimited(data, outcome, None, off, first, rel_ends=ends, at_eof=last and status == 0)
+                if last:
+                    break
+        finally:
+            eng.batch_cancel()
+            t.join()
+            if held is not None:
+                eng.release_batch(held)
+            eng.batch_end()
+        if err:
+            raise err[0]
 
     def ref_iter(self) -> RecordRefIter:
         return RecordRefIter(self._chunks())
@@ -297,29 +424,88 @@ class Parser:
         False if the closure stopped; raises FastqError -- after all earlier records were
         delivered -- on bad input."""
         it = self.ref_iter()
-        while True:
-            it.advance()
-            rec = it.get()
-            if rec is None:
-                return True
-            if not func(rec):
-                return False
+        try:
+            while True:
+                it.advance()
+                rec = it.get()
+                if rec is None:
+                    return True
+                if not func(rec):
+                    return False
+        finally:
+            it.close()
 
     def record_sets(self) -> Iterator[RecordSet]:
-        """Batches of records whose bytes span at most BUFSIZE (src/lib.rs:364-425).  As in the
-        reference, an error surfaces when the batch holding the bad record would be produced,
-        and that batch is dropped."""
+        """The RecordSets the reference's RecordSetIter yields (src/lib.rs:364-425) -- same composition, same
+        error behaviour -- rebuilt from the GPU's record index: a set = the records that are complete inside one
+        fill of the reference's 68 KiB buffer.  With a reader that fills every read() the fills follow from the
+        record boundaries alone (src/buffer.rs:30-48,74-100): the incomplete record is parked so that it ends on
+        a 16-byte boundary and the next read adds n_free rounded down to 4096 (all of it below 4096).  The first
+        set is empty (the buffer starts empty, src/lib.rs:381-391).  On bad input the records of the fill in
+        which the error is DETECTED are dropped (src/lib.rs:375,399-410) and the error is raised; records of
+        earlier fills have been yielded.  Every set owns a copy of its bytes, like the reference's."""
+        fill_end = 0                       # stream offset up to which the reference's buffer has been filled
+        pend: list = []                    # (bytes, start, e0..e3) of the records of the fill being built (stream offsets)
+        first = True
+        total_end = None                   # stream length, known at the end
+        last = None
         for d in self._chunks():
+            last = d
             n = len(d.starts)
             i = 0
             while i < n:
-                j = int(np.searchsorted(d.ends[:, 3], d.starts[i] + BUFSIZE - 1, side="right"))
-                j = max(j, i + 1)
-                if j >= n and d.outcome.status != 0:
-                    break  # the batch that would end at the bad record is dropped (src/lib.rs:375,399-410)
-                yield RecordSet(d.buf, d.starts[i:j], d.ends[i:j])
-                i = j
-            d.raise_for_status()
+                s_abs, e_abs = d.base + int(d.starts[i]), d.base + int(d.ends[i, 3])
+                if first:                  # the empty first set: the first fill happens inside the first next()
+                    first = False
+                    fill_end = BUFSIZE
+                    yield RecordSet(memoryview(b""), np.empty(0, np.int64), np.empty((0, 4), np.int64))
+                if e_abs < fill_end:       # complete inside the current fill
+                    pend.append((bytes(d.buf[int(d.starts[i]):int(d.ends[i, 3]) + 1]), s_abs, d.ends[i] + d.base))
+                    i += 1
+                    continue
+                # Incomplete (or EmptyBuffer at e_abs + 1 == ... ): the set goes out, the buffer is refilled
+                yield _owned_set(pend)
+                pend = []
+                fill_end = _next_fill(fill_end, s_abs)
+            if d.outcome.status != 0 or d.at_eof:
+                break
+        if last is None:
+            return
+        o = last.outcome
+        if first:                          # no record at all: the reference still fills once (and that set is all
+            fill_end = BUFSIZE             # there is if the input is empty: reader_at_end, src/lib.rs:386-388)
+            yield RecordSet(memoryview(b""), np.empty(0, np.int64), np.empty((0, 4), np.int64))
+            if o.status == 0 and len(last.buf) == 0:
+                return
+        stream_end = last.base + len(last.buf)        # (what the host has seen of the stream: enough for the checks below)
+        if o.status == 0:
+            # clean end: the pending set goes out when the buffer runs empty; one more (empty) set follows if that
+            # refill still found bytes... it cannot at EOF: reader_at_end (src/lib.rs:386-388)
+            yield _owned_set(pend)
+            return
+        # where the reference detects the error, relative to the fills
+        e = o.err_offset
+        while True:
+            det = _detect_point(last, o.status, e)    # stream offset of the byte whose presence triggers the Err
+            if o.status in (4, 5) or det is None or det >= fill_end:
+                # Incomplete in this fill: the set goes out first (unless this very call raises too long / truncated)
+                if o.status in (4, 5):
+                    # too long: raised by the call that finds the buffer full (n_free() == 0 after parking it);
+                    # truncated: by the call whose read returns 0.  Either way the records of that call are dropped
+                    # -- but earlier fills that merely found the record incomplete went out.
+                    nxt = _next_fill(fill_end, e)
+                    if nxt == fill_end or fill_end >= stream_end:
+                        break              # this call raises: pending records dropped
+                    yield _owned_set(pend)
+                    pend = []
+                    fill_end = nxt
+                    continue
+                yield _owned_set(pend)
+                pend = []
+                fill_end = _next_fill(fill_end, e)
+                continue
+            break                          # detected inside the current fill: its records are dropped
+        last.raise_for_status()
 
     def parallel_each(self, n_threads: int, func: Callable[[Iterator[RecordSet]], object]) -> list:
         """n_threads workers, each fed RecordSets round-robin over a bounded channel of 10
@@ -451,19 +637,23 @@ def each_zipped(parser1: Parser, parser2: Parser, callback) -> tuple[bool, bool]
     """src/lib.rs:577-609, lock-step over two delimited streams."""
     it1, it2 = parser1.ref_iter(), parser2.ref_iter()
     finished = (False, False)
-    it1.advance()
-    it2.advance()
-    while True:
-        v1 = None if finished[0] else it1.get()
-        v2 = None if finished[1] else it2.get()
-        finished = (v1 is None, v2 is None)
-        adv = callback(v1, v2)
-        if tuple(adv) == (False, False) or finished == (True, True):
-            return finished
-        if adv[0] and not finished[0]:
-            it1.advance()
-        if adv[1] and not finished[1]:
-            it2.advance()
+    try:
+        it1.advance()
+        it2.advance()
+        while True:
+            v1 = None if finished[0] else it1.get()
+            v2 = None if finished[1] else it2.get()
+            finished = (v1 is None, v2 is None)
+            adv = callback(v1, v2)
+            if tuple(adv) == (False, False) or finished == (True, True):
+                return finished
+            if adv[0] and not finished[0]:
+                it1.advance()
+            if adv[1] and not finished[1]:
+                it2.advance()
+    finally:
+        it1.close()
+        it2.close()
 
 
 def parse_path(path, func, max_len: int = 150):

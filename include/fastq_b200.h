@@ -39,6 +39,7 @@ enum {
     FQB_E_ARG = 50,      /* bad argument (null pointer, misaligned buffer, ...) */
     FQB_E_STATE = 51,    /* call out of order (e.g. submit without acquire) */
     FQB_E_NOMEM = 52,
+    FQB_E_CANCELLED = 53, /* batch mode: fqb_batch_cancel was called (the closure returned false) */
     FQB_E_CUDA = 100,    /* CUDA runtime failure; fqb_last_error() has the text */
     FQB_E_NCCL = 101     /* NCCL missing or failing (multi-rank entry points only); fqb_last_error() */
 };
@@ -87,7 +88,7 @@ typedef struct {
     uint32_t max_len;       /* P: positions tracked per read (150, 300, ...), 1..4096 */
     uint32_t reserved0;
     uint64_t slot_bytes;    /* streaming: bytes per pinned/device ring slot (0 = 64 MiB) */
-    uint32_t n_slots;       /* streaming: ring depth (0 = 3); mirrors thread_reader's queuelen
+    uint32_t n_slots;       /* streaming: ring depth (0 = 4); mirrors thread_reader's queuelen
                                (src/thread_reader.rs:13-32) */
     uint32_t reserved1;
 } fqb_config;
@@ -218,6 +219,41 @@ int fqb_stream_acquire(fqb_ctx *ctx, uint8_t **pinned, uint64_t *cap);
 int fqb_stream_submit(fqb_ctx *ctx, uint64_t n_valid);
 /* end of input: drains the ring, returns outcome + stats */
 int fqb_stream_finish(fqb_ctx *ctx, fqb_result *res, uint64_t *host_stats);
+
+/* ---- batch mode: the generic-closure path, asynchronous --------------------------------------------
+ * replaces RecordSetIter::next / RecordSet (src/lib.rs:306-426) and what parallel_each's producer loop does with
+ * them (src/lib.rs:509-566): the GPU delimits chunk after chunk while the caller's closures run over the
+ * chunks already delimited.
+ *   producer thread: fqb_batch_begin; then, per read() of the input, fqb_stream_acquire -> fill -> fqb_stream_submit
+ *                    (the thread_reader protocol, as in the streaming ring); fqb_batch_close at the end of the input
+ *   consumer thread: fqb_next_batch -> the records of one chunk: their bytes (borrowed from the pinned host ring:
+ *                    valid until fqb_release_batch, the lifetime rule of RecordSet's own buffer) and, per record,
+ *                    the four line ends of IdxRecord (src/records.rs:56-63) -- low 32 bits of stream offsets;
+ *                    offset within `bytes` = (uint32_t)(line_end - (uint32_t)stream_offset).
+ * The shim deals sub-ranges of a batch to its worker threads exactly as src/lib.rs:535 deals RecordSets.
+ * At most n_slots - 3 batches may be held (not yet released) at a time; fqb_config.n_slots >= 4.
+ * A batch with status != FQB_OK is the last one: its n_records records precede the bad record (each() delivers
+ * them, src/lib.rs:226-237), err_offset is the stream offset of the bad one. */
+typedef struct {
+    const uint8_t *bytes;      /* first byte of the first record of the batch (pinned host memory) */
+    uint64_t n_bytes;          /* bytes[0 .. n_bytes) = the records, back to back */
+    uint64_t n_avail;          /* >= n_bytes: stream bytes readable from `bytes` on (what follows the records: the
+                                  bad record of a batch with status != FQB_OK, for diagnostics) */
+    uint64_t stream_offset;    /* stream offset of bytes[0] */
+    const uint32_t *line_ends; /* 4 x n_records entries */
+    uint64_t n_records;
+    uint64_t first_record;     /* records handed out before this batch */
+    uint64_t err_offset;
+    uint64_t token;            /* for fqb_release_batch (UINT64_MAX: an empty end-of-input marker, nothing to release) */
+    int32_t status;
+    int32_t last;              /* 1 = no batch follows (end of input, or status != FQB_OK) */
+} fqb_batch;
+int fqb_batch_begin(fqb_ctx *ctx, uint32_t flags);    /* flags: 0 or FQB_F_HIST (statistics alongside, via fqb_batch_end) */
+int fqb_batch_close(fqb_ctx *ctx);                    /* producer: end of input */
+int fqb_next_batch(fqb_ctx *ctx, fqb_batch *out);     /* consumer: blocks until the next batch is ready */
+int fqb_release_batch(fqb_ctx *ctx, uint64_t token);  /* consumer (any thread): RecordSet dropped */
+int fqb_batch_cancel(fqb_ctx *ctx);                   /* either side: stop early; blocked calls return FQB_E_CANCELLED */
+int fqb_batch_end(fqb_ctx *ctx, fqb_result *res);     /* after the last batch / cancel, producer thread joined */
 
 /* ---- N ranks, one byte shard per GPU: the one collective of the path ---------------------------
  * The reference has nothing to shard (parallel_each delimits on ONE thread, src/lib.rs:535); this is the

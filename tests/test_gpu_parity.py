@@ -1025,6 +1025,71 @@ def test_each_over_a_reader_in_refills(chunk, fq, oracle, eng):
         assert n_sets <= ores.n_records and (ores.status != 0 or n_sets == ores.n_records)
 
 
+@pytest.fixture(scope="module")
+def eng_small_slots(fq):
+    e = fq.Engine(max_len=150, slot_bytes=160 * 1024, n_slots=4)      # many batches, records that straddle slots
+    yield e
+    e.close()
+
+
+class _FailingReader:
+    def __init__(self, data, fail_at):
+        self._b, self._n, self._fail_at = io.BytesIO(data), 0, fail_at
+
+    def read(self, n):
+        if self._n >= self._fail_at:
+            raise OSError("disk on fire")
+        b = self._b.read(min(n, 50000))
+        self._n += len(b)
+        return b
+
+
+def test_batch_mode_each_and_record_sets(fq, oracle, eng_small_slots):
+    """The asynchronous generic-closure path (fqb_batch_begin / fqb_next_batch / fqb_release_batch): a reader
+    thread feeds the pinned ring while the caller walks the batches already delimited.  Records, their order, the
+    error and the RecordSets equal the oracle's each() / record_sets()."""
+    e = eng_small_slots
+    recs = [_rec(i, L) for i, L in enumerate([150, 0, 3, 150, 30000, 151, 150, 1, 34000, 150, 20000, 7] * 12)]
+    good = b"".join(recs)
+    cases = [good, good[:-1], good + b"\n", good[:len(good) // 2] + b"X" + good[len(good) // 2:], good + b"@tail\nAC\n",
+             good + _rec(99, 40000) + _rec(100, 5), b"", b"@a\nA\n+\nI\n", good[:321 * 3]]
+    for k, data in enumerate(cases):
+        ores, oidx = oracle.each_index(data)
+        for with_readinto in (False, True):
+            seen, err = [], None
+            try:
+                fin = fq.Parser(_ShortReader(data, with_readinto), engine=e).each(
+                    lambda r: seen.append((bytes(r.data), r.head(), r.seq(), r.qual())) or True)
+                assert fin is True
+            except fq.FastqError as ex:
+                err = ex
+            assert len(seen) == ores.n_records, (k, len(seen), ores.n_records)
+            assert (err.status if err else 0) == ores.status, k
+            if err:
+                assert err.offset == ores.err_offset and err.n_delivered == ores.n_records
+            for i, (raw, head, seq, qual) in enumerate(seen):
+                s, e0, e1, e2, e3 = (int(x) for x in oidx[i])
+                assert raw == data[s:e3 + 1] and head == data[s + 1:e0] and seq == data[e0 + 1:e1] and qual == data[e2 + 1:e3]
+        ostatus, osets = oracle.record_sets(data)
+        sets, serr = [], 0
+        try:
+            for s in fq.Parser(io.BytesIO(data), engine=e).record_sets():
+                sets.append([bytes(r.data) for r in s.iter()])
+        except fq.FastqError as ex:
+            serr = ex.status
+        assert serr == ostatus
+        assert sets == [[r.raw for r in x] for x in osets], k
+    # early stop: the closure says no, the reader thread is told to stop, the context is reusable at once
+    n = []
+    assert fq.Parser(io.BytesIO(good), engine=e).each(lambda r: n.append(1) or len(n) < 5) is False and len(n) == 5
+    assert fq.Parser(io.BytesIO(good), engine=e).count() == len(recs)
+    # a reader that fails: its error reaches the caller, after the records in front of it
+    with pytest.raises(OSError):
+        fq.Parser(_FailingReader(good, 300000), engine=e).each(lambda r: True)
+    out = fq.Parser(io.BytesIO(good), engine=e).parallel_each(3, lambda sets: sum(s.len() for s in sets))
+    assert sum(out) == len(recs)
+
+
 def test_each_zipped_over_readers(fq, oracle, eng):
     """src/lib.rs:577-609 over two readers consumed in refills of different sizes."""
     a = oracle.synth_fixed_records(3000).tobytes()

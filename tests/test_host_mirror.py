@@ -148,3 +148,68 @@ def test_each_zipped_propagates_errors_of_either_stream():
     for a, b in ((good, bad), (bad, good)):
         with pytest.raises(FastqError):
             fqp.each_zipped(_parser(a, 50), _parser(b, 50), lambda r1, r2: (True, True))
+
+
+# ---- record_sets: same sets, same dropped records, same error as the reference's RecordSetIter --------------
+def _sets_of(parser):
+    out, err = [], 0
+    try:
+        for s in parser.record_sets():
+            out.append([bytes(r.data) for r in s.iter()])
+    except FastqError as e:
+        err = e.status
+    return err, out
+
+
+def _long(i, n):
+    """a record of exactly n bytes"""
+    return b"@" + b"h" * (n - 8) + b"\nA\n+\nB\n"
+
+
+RS_CASES = {
+    "empty": b"",
+    "one": _rec(0, 150),
+    "many_fixed": b"".join(_rec(i, 150) for i in range(1500)),
+    "many_var": b"".join(_rec(i, 10 + (i * 37) % 400) for i in range(1200)),
+    "exactly_bufsize": _long(0, 68 * 1024),
+    "bufsize_then_more": _long(0, 68 * 1024) + b"".join(_rec(i, 99) for i in range(300)),
+    "long_records": b"".join(_long(i, n) for i, n in enumerate([30000, 40000, 69000, 8, 69616, 50, 69600])),
+    "too_long_mid": b"".join(_rec(i, 150) for i in range(400)) + _long(0, 70000) + _rec(1, 5),
+    "too_long_band": _rec(0, 7) + _long(0, 69625) + _rec(1, 5),
+    "truncated": b"".join(_rec(i, 150) for i in range(500))[:-1],
+    "truncated_tail_record": b"".join(_rec(i, 150) for i in range(500)) + b"@tail\nACGT\n",
+    "bad_header_mid": b"".join(_rec(i, 150) for i in range(700)) + b"X" + b"".join(_rec(i, 150) for i in range(50)),
+    "bad_sep": b"".join(_rec(i, 150) for i in range(650)) + b"@x\nACGT\n-\nIIII\n" + _rec(9, 9),
+    "bad_len": b"".join(_rec(i, 150) for i in range(333)) + b"@x\nACGT\n+\nIII\n" + _rec(9, 9),
+    "blank_line_end": b"".join(_rec(i, 150) for i in range(100)) + b"\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(RS_CASES))
+@pytest.mark.parametrize("chunk", [None, 100000, 4097])
+def test_record_sets_match_the_reference_fills(name, chunk):
+    data = RS_CASES[name]
+    ostatus, osets = oracle.record_sets(data)
+    err, sets = _sets_of(_parser(data, chunk))
+    assert err == ostatus, (name, err, ostatus)
+    assert [len(x) for x in sets] == [len(x) for x in osets], name
+    assert [[r for r in x] for x in sets] == [[r.raw for r in x] for x in osets]
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.integers(0, 1200), min_size=0, max_size=300), st.integers(0, 3), st.sampled_from([None, 50000]))
+def test_record_sets_fuzz_against_the_oracle(lens, damage, chunk):
+    recs = [_rec(i, L) for i, L in enumerate(lens)]
+    data = b"".join(recs)
+    if damage == 1 and data:
+        data = data[:len(data) * 2 // 3]
+    elif damage == 2 and len(recs) > 2:
+        k = len(b"".join(recs[:len(recs) // 2]))
+        data = data[:k] + b"#" + data[k + 1:]
+    elif damage == 3 and len(recs) > 2:
+        k = len(b"".join(recs[:len(recs) // 2])) + recs[len(recs) // 2].index(b"\n+\n") + 1
+        data = data[:k] + b"-" + data[k + 1:]
+    ostatus, osets = oracle.record_sets(data)
+    err, sets = _sets_of(_parser(data, chunk))
+    assert err == ostatus
+    assert [[r for r in x] for x in sets] == [[r.raw for r in x] for x in osets]
