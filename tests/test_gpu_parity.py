@@ -1090,6 +1090,34 @@ def test_batch_mode_each_and_record_sets(fq, oracle, eng_small_slots):
     assert sum(out) == len(recs)
 
 
+def test_c_program_drives_the_batch_mode(oracle, tmp_path):
+    """tests/c/batch_each.c: a plain C program (pthread producer + consumer loop) over the C ABI -- no Python, no
+    torch in the process -- against the oracle's each(): record count, bases, a hash over every record byte, error."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "batch_each")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(HERE, "c", "batch_each.c"),
+                           "-o", exe, "-L", os.path.join(root, "fastq_rs_b200"), "-l:libfastq_b200.so", "-lpthread",
+                           "-Wl,-rpath," + os.path.join(root, "fastq_rs_b200")])
+    good = oracle.synth_fixed_records(40000).tobytes() + b"".join(_rec(i, L, crlf=(i % 2 == 0)) for i, L in enumerate([5, 30000, 0, 151] * 20))
+    for k, data in enumerate((good, good[:-7], good[:5000000] + b"?" + good[5000000:], b"")):
+        path = tmp_path / f"in{k}.fastq"
+        path.write_bytes(data)
+        out = subprocess.run([exe, str(path), "1024"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        status, n_rec, n_bases, fnv, err_off, n_batches = (int(x) for x in out.stdout.split())
+        res, recs = oracle.each(data)
+        bases = sum(len(r.seq) for r in recs)
+        end = (recs[-1].offset + len(recs[-1].raw)) if recs else 0
+        arr = np.frombuffer(data, dtype=np.uint8)[:end].astype(np.uint64)        # the delivered records, back to back
+        with np.errstate(over="ignore"):
+            chk = int((arr.sum() * np.uint64(1000003) + (arr * np.arange(1, end + 1, dtype=np.uint64)).sum()) & np.uint64(0xFFFFFFFFFFFFFFFF)) if end else 0
+        assert (status, n_rec, n_bases, fnv) == (res.status, res.n_records, bases, chk), (k, out.stdout)
+        if res.status:
+            assert err_off == res.err_offset
+        assert n_batches >= max(1, (res.err_offset if res.status else len(data)) >> 20), out.stderr
+
+
 def test_each_zipped_over_readers(fq, oracle, eng):
     """src/lib.rs:577-609 over two readers consumed in refills of different sizes."""
     a = oracle.synth_fixed_records(3000).tobytes()
