@@ -14,7 +14,7 @@ SO_PATH = os.environ.get("FQB_LIB") or os.path.join(_HERE, "libfastq_b200.so")  
 ABI_VERSION = int(os.environ.get("FQB_ABI", "3"))   # (FQB_ABI: A/B runs against an older build, tools/)
 
 # status codes (include/fastq_b200.h)
-OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE = range(8)
+OK, E_HEADER, E_SEP, E_LENGTH, E_TOO_LONG, E_TRUNCATED, E_IO, E_PHASE, E_RETRY = range(9)
 E_ARG, E_STATE, E_NOMEM, E_CANCELLED, E_CUDA, E_NCCL = 50, 51, 52, 53, 100, 101
 MAX_WORLD, COMM_ID_BYTES = 64, 128
 KEEP_ALL, KEEP_DNA, KEEP_DNAN = 0, 1, 2

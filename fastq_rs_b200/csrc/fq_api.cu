@@ -7,6 +7,7 @@
 //   thread_reader (2-queue ring)  src/thread_reader.rs:8-200 -> pinned slots: acquire / submit / recycle on event
 #include "../../include/fastq_b200.h"
 #include "fq_common.cuh"
+#include "fq_device.cuh"
 
 #include <dlfcn.h>
 
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(32) fq_init_kernel(DevResult* r, int spec_fail
     r->line_phase = line_phase;
     r->n_win_pred = 0;
     r->n_win_scan = 0;
+    r->spec_bad = NONE64;
+    r->spec_retry = 0;
     r->tail_err = 0;
 }
 
@@ -118,6 +121,46 @@ __global__ void __launch_bounds__(256) fq_batch_out_kernel(const uint32_t* __res
         info[5] = r->tail_start == NONE64 ? 0ull : r->tail_start + 1ull;
         info[6] = 0;
         info[7] = 0;
+    }
+}
+
+// ---- a bad record in the middle of a shard (DevResult::spec_retry): after the bytes in front of it have been parsed
+// again on their own, these put the outcome of the WHOLE shard together: the bad record is classified
+// (fq_diagnose_kernel), the '\n' behind it still count as lines of the shard, the outcome is published anew
+__global__ void fq_retry_mark_kernel(DevResult* r, unsigned long long x)
+{
+    r->first_bad = x;
+    r->tail_err = 1;     // (nothing behind it was counted: no restricted second pass needed)
+}
+__global__ void __launch_bounds__(256) fq_tail_lines_kernel(const uint8_t* __restrict__ d, unsigned long long x,
+                                                            unsigned long long n_own, DevResult* r)
+{
+    const unsigned long long xa = min(n_own, (x + 15ull) & ~15ull), ne = xa + ((n_own - xa) & ~15ull);
+    unsigned long long cnt = 0;
+    const unsigned long long gt = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = xa / 16 + gt; i < ne / 16; i += stride) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(d) + i);
+        cnt += __popc(nlbits(v.x)) + __popc(nlbits(v.y)) + __popc(nlbits(v.z)) + __popc(nlbits(v.w));
+    }
+    if (gt < xa - x) cnt += d[x + gt] == '\n';                   // the bytes in front of the first aligned piece
+    if (gt < n_own - ne) cnt += d[ne + gt] == '\n';              // ... and behind the last one
+    cnt = warp_sum_u64(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&r->n_lines, cnt);
+        atomicAdd(&r->line_end, cnt);
+    }
+}
+__global__ void fq_republish_kernel(const ScanParams p, unsigned long long* pub, unsigned long long* slot)
+{
+    DevResult* r = p.res;
+    r->finished = 0;
+    r->tail_err = 0;
+    unsigned long long w[8] = {(unsigned long long)r->status, 0ull, r->n_records, r->n_lines, r->err_offset,
+                               NONE64, (unsigned long long)r->line_phase, 0ull};
+    for (int k = 0; k < 8; ++k) {
+        if (pub) pub[k] = w[k];
+        if (slot) slot[k] = w[k];
     }
 }
 
@@ -170,6 +213,8 @@ struct fqb_ctx {
     unsigned long long* d_trace = nullptr;  // FQB_TRACE=<file>: kernel timeline, dumped by fqb_fetch
     std::string trace_path;
     uint64_t last_off = 0;
+    fqb_shard last_shard = {};     // of the last fqb_parse_device (fqb_fetch may have to parse a part of it again)
+    uint64_t retries = 0;          // 1 if fqb_fetch did
     std::string err;
     // streaming
     uint64_t slot_bytes = 0;
@@ -389,7 +434,7 @@ void fqb_destroy(fqb_ctx* ctx)
 //   records before it: each() delivers exactly those, src/lib.rs:226-237]
 //   -> index compaction (speculative kernel only) -> finalize
 static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, DevCarry* carry, uint64_t* total,
-                         bool timed)
+                         bool timed, bool allow_retry = false)
 {
     if (!sh || sh->n_avail < sh->n_own) return FQB_E_ARG;
     if (sh->n_avail && (!sh->d_bytes || (reinterpret_cast<uintptr_t>(sh->d_bytes) & 15))) return FQB_E_ARG;
@@ -419,7 +464,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             const uint64_t need = live * stage_share;
             if (need > ctx->index_stage_cap) {
                 if (ctx->d_index_stage) {
-                    CK(cudaStreamSynchronize(st));
+                    // (an earlier parse of this context may still be using the staging area on ANOTHER stream)
+                    CK(cudaDeviceSynchronize());
                     CK(cudaFree(ctx->d_index_stage));
                     ctx->d_index_stage = nullptr;
                     ctx->index_stage_cap = 0;
@@ -438,6 +484,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.line_base = sh->line_base;
     p.carry = carry;
     p.flags = (sh->flags & (F_HIST | F_INDEX | F_LINE_START | F_EOF | F_FRONT16 | F_INFER_START)) | (carry ? F_CARRY : 0);
+    if (allow_retry && !carry && !getenv("FQB_NO_RETRY")) p.flags |= F_CAN_RETRY;
     if ((p.flags & F_INFER_START) && carry) return FQB_E_ARG;   // a stream knows its line numbers
     if ((p.flags & F_FRONT16) && (p.flags & F_LINE_START)) return FQB_E_ARG;
     p.max_len = ctx->P;
@@ -513,7 +560,9 @@ int fqb_parse_device(fqb_ctx* ctx, const fqb_shard* shard, void* stream)
 {
     if (!ctx || !shard) return FQB_E_ARG;
     ctx->last_off = shard->stream_offset;
-    return enqueue_parse(ctx, shard, static_cast<cudaStream_t>(stream), nullptr, nullptr, true);
+    ctx->last_shard = *shard;
+    ctx->retries = 0;
+    return enqueue_parse(ctx, shard, static_cast<cudaStream_t>(stream), nullptr, nullptr, true, true);
 }
 
 static void fill_result(const DevResult* r, uint64_t stream_offset_of_tail_base, fqb_result* res)
@@ -536,6 +585,36 @@ int fqb_fetch(fqb_ctx* ctx, void* stream, fqb_result* res, uint64_t* host_stats)
     CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, st));
     if (host_stats) CK(cudaMemcpyAsync(host_stats, ctx->d_stats, ctx->nwords * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->h_res->spec_retry && !ctx->h_res->spec_fail) {
+        // A record in the middle of the shard fails validation, and the speculative kernel has proved that everything
+        // in front of it (offset X) is delimited as a sequential parse would.  Its counters, though, include records
+        // BEHIND the bad one, which each() never delivers (src/lib.rs:226-237).  So: the bytes [0, X) once more, as a
+        // shard of their own (a clean parse of a shorter input), then the bad record is classified in the reference's
+        // check order and the '\n' behind it are counted.  Twice a clean parse at most, instead of the exact path.
+        const unsigned long long X = ctx->h_res->spec_bad;
+        fqb_shard sh = ctx->last_shard;
+        sh.n_own = sh.n_avail = X;
+        int rc = enqueue_parse(ctx, &sh, st, nullptr, nullptr, false, false);
+        if (rc) return rc;
+        ScanParams p;
+        memset(&p, 0, sizeof p);
+        p.data = ctx->last_shard.d_bytes;
+        p.n_own = ctx->last_shard.n_own;
+        p.n_avail = ctx->last_shard.n_avail;
+        p.stream_offset = ctx->last_shard.stream_offset;
+        p.flags = ctx->last_shard.flags & (F_EOF | F_INFER_START);
+        p.res = ctx->d_res;
+        fq_retry_mark_kernel<<<1, 1, 0, st>>>(ctx->d_res, X);
+        CK(launch_diagnose(p, nullptr, st));
+        fq_tail_lines_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(p.data, X, p.n_own, ctx->d_res);
+        fq_republish_kernel<<<1, 1, 0, st>>>(p, ctx->d_pub, reinterpret_cast<unsigned long long*>(ctx->d_stats) + ctx->nwords + 8 * (size_t)ctx->rank);
+        CK(cudaGetLastError());
+        ctx->launches += 4;
+        ctx->retries = 1;
+        CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, st));
+        if (host_stats) CK(cudaMemcpyAsync(host_stats, ctx->d_stats, ctx->nwords * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     if (ctx->d_trace) {
         std::vector<unsigned long long> h((size_t)ctx->num_sms * TRACE_K * 16);
         CK(cudaMemcpy(h.data(), ctx->d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -643,7 +722,7 @@ int fqb_fetch_filter(fqb_ctx* ctx, void* stream, uint64_t* n_kept, uint64_t* out
 int fqb_last_path(fqb_ctx* ctx, uint64_t out[3])
 {
     if (!ctx || !out || !ctx->h_res) return FQB_E_ARG;
-    out[0] = ctx->h_res->spec_fail ? 1 : 0;
+    out[0] = (ctx->h_res->spec_fail ? 1 : 0) | (ctx->retries ? 2 : 0);   // bit 1: the part in front of a bad record was parsed twice
     out[1] = ctx->h_res->n_win_pred;
     out[2] = ctx->h_res->n_win_scan;
     return FQB_OK;

@@ -31,6 +31,9 @@ constexpr uint32_t F_HIST = 0x01, F_INDEX = 0x02, F_LINE_START = 0x04, F_EOF = 0
 constexpr uint32_t F_INFER_START = 0x20;   // the phase of line_base is unknown: range 0 infers its first record too
 constexpr uint32_t F_RERUN = 0x100;        // internal: second pass restricted to records before first_bad
 constexpr uint32_t F_CARRY = 0x200;        // internal: streaming, line_base comes from the carry block
+constexpr uint32_t F_CAN_RETRY = 0x400;    // internal: a record that fails validation in the middle of the shard ends its
+                                           // range there (spec_bad) instead of voiding the launch: the host parses the bytes
+                                           // in front of it again (fqb_fetch), see fq_stream_verify_kernel
 
 
 // device-resident outcome of one parse (mirrors fqb_result, plus scratch)
@@ -48,6 +51,10 @@ struct DevResult {
     unsigned long long n_win_pred;  // windows of the speculative kernel that were predicted / scanned (FQB_DEBUG)
     unsigned long long n_win_scan;
     int tail_err;                   // the speculative kernel itself found the first bad record: it lies in the last
+    unsigned long long spec_bad;    // smallest offset at which a range of the speculative kernel stopped at a record that
+                                    // fails validation (F_CAN_RETRY); spec_retry: fq_stream_verify_kernel has confirmed
+    int spec_retry;                 // that every record in front of it is delimited as a sequential parse would
+    int pad3;
     int shape_var;                  // range of an EOF shard, so nothing behind it was counted; first_bad holds it
                                     // shape_var: the head of the shard holds reads of varying length (fq_init_kernel):
                                     // the speculative kernel's variant for such input does the work

@@ -198,6 +198,9 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
             // an inferred shard start the speculative kernel could not stand by: the caller must come
             // back with the exact line_base (FQB_E_PHASE)
             if ((p.flags & F_INFER_START) && r->spec_fail) r->status = 7;
+            // a bad record in the middle of the shard, everything in front of it verified: the numbers of this
+            // launch include records behind it -- the caller fetches (fqb_fetch parses the bytes in front of it again)
+            if (r->spec_retry) r->status = 8;
             r->n_records = p.stats[0];
             r->finished = r->status == 0 ? 1 : 0;
             if (pub) {   // the outcome as 8 device-resident words (fqb_device_result)

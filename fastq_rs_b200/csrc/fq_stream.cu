@@ -885,7 +885,7 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
             break;
         }
         if (first_bad != NO_START) {
-            if (!last_eof) {
+            if (!last_eof && !(p.flags & F_CAN_RETRY)) {
                 rs.failed = true;   // a record that fails validation: the exact path finds and classifies it
                 break;
             }
@@ -1260,7 +1260,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
                     first_bad = stream_pass<C, HIST>(p, buf, buf_s, lc, hist_s, lenh, Pm, n_rec, pass, wa, sub, li);
                 if (first_bad != NO_START) {
-                    if (!last_eof) {
+                    if (!last_eof && !(p.flags & F_CAN_RETRY)) {
                         failed = true;   // a record that fails validation: the exact path finds and classifies it
                         break;
                     }
@@ -1354,21 +1354,31 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             if (tail_x != NONE64) break;
             if (HIST) drain_tick<C>(hist, p, cta, n_rec, my_epoch, warp, lane);   // u16 counter halves
         }
+        bool stopped = false;
         if (tail_x != NONE64 && !failed) {
-            // (the line ends of the bytes behind it are counted and indexed by fq_tail_index_kernel)
-            if (lane == 0) {
-                atomicMin(&p.res->first_bad, tail_x);
-                p.res->tail_err = 1;
+            if (last_eof) {
+                // (the line ends of the bytes behind it are counted and indexed by fq_tail_index_kernel)
+                if (lane == 0) {
+                    atomicMin(&p.res->first_bad, tail_x);
+                    p.res->tail_err = 1;
+                }
+                cur = p.n_avail;
+            } else {
+                // a bad record in the middle of the shard: this range ends in front of it; the ranges behind it have
+                // counted records that each() never delivers -- the bytes in front of the smallest such offset are
+                // parsed again once the chain of the ranges up to here has been verified (fq_stream_verify_kernel)
+                if (lane == 0) atomicMin(&p.res->spec_bad, tail_x);
+                cur = tail_x;
+                stopped = true;
             }
-            cur = p.n_avail;
         }
         // data that ends inside the owned bytes without a record boundary: not a clean shard
-        if (!failed && cur < R1) failed = true;
+        if (!failed && !stopped && cur < R1) failed = true;
         if (lane == 0) {
             StreamRange& sr = p.sranges[rid];
             sr.end = cur;
             sr.n_lines = lrank;
-            sr.flags = failed ? 2u : 1u;
+            sr.flags = failed ? 2u : (stopped ? 3u : 1u);
             atomicAdd(&p.res->n_win_pred, (unsigned long long)dbg_pred);
             atomicAdd(&p.res->n_win_scan, (unsigned long long)dbg_scan);
             if (failed) atomicExch(&p.res->spec_fail, 1);
@@ -1400,32 +1410,44 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
 __global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams p, const DevCarry* carry)
 {
     __shared__ unsigned long long part[1024];
-    __shared__ int fail_s;
+    __shared__ unsigned int first_fail_s, first_stop_s;
     if (p.res->spec_fail) return;
     if (carry && carry->status != 0) return;
     const unsigned long long line_base = carry ? carry->line_base : p.line_base;
     const int t = threadIdx.x;
     const uint32_t nlive = p.n_sranges;
     const uint32_t per = (nlive + 1023u) / 1024u;
-    if (t == 0) fail_s = 0;
+    if (t == 0) {
+        first_fail_s = 0xFFFFFFFFu;
+        first_stop_s = 0xFFFFFFFFu;
+    }
     __syncthreads();
     unsigned long long sum = 0;
-    int fail = 0;
+    // first range that did not deliver (or whose chain to its predecessor is broken), first range that stopped at
+    // a bad record (F_CAN_RETRY): everything in front of the smaller of the two is verified
+    uint32_t my_fail = 0xFFFFFFFFu, my_stop = 0xFFFFFFFFu;
     for (uint32_t k = 0; k < per; ++k) {
         const uint32_t r = (uint32_t)t * per + k;
         if (r >= nlive) break;
         const StreamRange sr = p.sranges[r];
         sum += sr.n_lines;
-        if (sr.flags != 1u) fail = 1;
-        if (r + 1 < nlive) {
-            if (p.sranges[r + 1].first != sr.end) fail = 1;
-        } else if (sr.end < p.n_own || ((p.flags & F_EOF) && sr.end != p.n_avail)) {
-            fail = 1;
+        if (sr.flags == 3u) my_stop = min(my_stop, r);
+        if (sr.flags != 1u && sr.flags != 3u) my_fail = min(my_fail, r);
+        if (sr.flags == 1u) {
+            if (r + 1 < nlive) {
+                if (p.sranges[r + 1].first != sr.end) my_fail = min(my_fail, r + 1u);
+            } else if (sr.end < p.n_own || ((p.flags & F_EOF) && sr.end != p.n_avail)) {
+                my_fail = min(my_fail, r);
+            }
         }
     }
     part[t] = sum;
-    if (fail) fail_s = 1;
+    if (my_fail != 0xFFFFFFFFu) atomicMin(&first_fail_s, my_fail);
+    if (my_stop != 0xFFFFFFFFu) atomicMin(&first_stop_s, my_stop);
     __syncthreads();
+    const bool retry = first_stop_s != 0xFFFFFFFFu && first_stop_s < first_fail_s;   // (a stopped range's own start is
+                                                                                    // covered by its predecessor's chain check)
+    const bool fail_any = !retry && first_fail_s != 0xFFFFFFFFu;
     // exclusive prefix over the 1024 partial sums (Hillis-Steele)
     for (int d = 1; d < 1024; d <<= 1) {
         const unsigned long long v = t >= d ? part[t - d] : 0ull;
@@ -1444,7 +1466,16 @@ __global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams
         p.res->n_lines = part[1023];
         p.res->line_end = line_base + part[1023];
     }
-    if (t == 0 && fail_s) p.res->spec_fail = 1;
+    if (t == 0) {
+        if (retry) {
+            // every record in front of sranges[first_stop].end is what a sequential parse delivers, and the record
+            // there fails validation: the host parses [0, that offset) again and classifies the record (fqb_fetch)
+            p.res->spec_retry = 1;
+            p.res->spec_bad = p.sranges[first_stop_s].end;
+        } else if (fail_any) {
+            p.res->spec_fail = 1;
+        }
+    }
 }
 
 // move the staged line ends of every range to their place in the caller's index (only when the

@@ -235,10 +235,11 @@ class Engine:
 
     def last_path(self) -> dict:
         """Which path produced the result of the last fetch(): {"exact": the speculative pass was abandoned,
-        "predicted": windows predicted, "scanned": windows scanned} (diagnostics)."""
+        "retried": a record in the middle of the shard was bad and the bytes in front of it were parsed a second time
+        (speculatively), "predicted": windows predicted, "scanned": windows scanned} (diagnostics)."""
         out = (C.c_uint64 * 3)()
         _check(self.ctx, self.L.fqb_last_path(self.ctx, C.byref(out)), "fqb_last_path")
-        return {"exact": bool(out[0]), "predicted": int(out[1]), "scanned": int(out[2])}
+        return {"exact": bool(out[0] & 1), "retried": bool(out[0] & 2), "predicted": int(out[1]), "scanned": int(out[2])}
 
     def last_scan_ms(self) -> float:
         return float(self.L.fqb_last_scan_ms(self.ctx))

@@ -28,7 +28,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import E_PHASE, OK
+from ._lib import E_PHASE, E_RETRY, OK
 from .engine import Outcome, Stats
 
 MAX_RECORD_BYTES = 68 * 1024
@@ -160,6 +160,10 @@ class ShardedParser:
             self.reparsed += 1      # the inference is not confirmed: parse again with the exact line number
             self._enqueue(sh, hist, index, line_base, False)
         # (a rank that does not parse again still has its block and outcome in the send buffer)
+        if self.native:
+            # FQB_E_RETRY in my slot (a bad record in the middle of my shard): fetch completes that parse and puts the
+            # final block and outcome into the send buffer; a no-op otherwise
+            self.eng.fetch(want_stats=False)
         _, g = self._reduce(want_stats=False)
         # first error in stream order wins; shards behind it contribute nothing
         bad = np.nonzero(g[:, 0] != OK)[0]

@@ -36,6 +36,11 @@ enum {
     FQB_E_IO = 6,        /* reader error passed through                src/buffer.rs:86-96    */
     FQB_E_PHASE = 7,     /* FQB_F_INFER_START: the first record of the shard could not be inferred
                             from its bytes; parse again with the exact line_base              */
+    FQB_E_RETRY = 8,     /* only ever seen in fqb_device_result / the outcome slots, never returned by fqb_fetch: a
+                            record in the middle of the shard is bad, every record in front of it is verified, but
+                            the device-resident numbers still include records behind it.  fqb_fetch completes the
+                            parse (the bytes in front of the bad record once more, then its classification);
+                            callers that read outcomes on the device call it when they see this status. */
     FQB_E_ARG = 50,      /* bad argument (null pointer, misaligned buffer, ...) */
     FQB_E_STATE = 51,    /* call out of order (e.g. submit without acquire) */
     FQB_E_NOMEM = 52,

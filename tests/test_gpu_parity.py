@@ -707,6 +707,57 @@ def test_variable_length_variant(what, torch, oracle, eng, eng300):
             assert not p["exact"], (what, engine.max_len, p)          # served by the fast path
 
 
+def test_mid_stream_error_costs_at_most_two_parses(torch, oracle, eng):
+    """A bad record in the middle of a big shard: the speculative kernel stops its range there, the ranges in front
+    are verified, and fqb_fetch parses the bytes in front of the bad record once more -- no exact pass, at most about
+    twice the time of a clean parse (it was ~7x through the exact path), results as the oracle's each()."""
+    n_rec = 1600000                                     # 514 MB of fixed 150 bp records
+    n = n_rec * 321
+    t = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    eng.synth_fixed(t, n)
+    idx = torch.zeros(4 * n_rec + 8, dtype=torch.int32, device="cuda")
+
+    def timed(hist):
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.parse_device(t, n_own=n, n_avail=n, hist=hist, index=idx)
+            out, st = eng.fetch(want_stats=hist)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best, out, st
+
+    for hist in (True, False):
+        clean_ms, out, _ = timed(hist)
+        assert out.status == 0 and out.n_records == n_rec
+        for where, kind in ((0.6, "at"), (0.97, "plus"), (0.3, "len")):
+            k = int(n_rec * where)
+            off = {"at": 321 * k, "plus": 321 * k + 17 + 151, "len": 321 * k + 17 + 151 + 2 + 150}[kind]
+            saved = t[off:off + 1].clone()
+            t[off] = {"at": ord("X"), "plus": ord("-"), "len": ord("A")}[kind]
+            err_ms, out, st = timed(hist)
+            p = eng.last_path()
+            assert (out.status, out.n_records, out.err_offset) == ({"at": 1, "plus": 2, "len": 3}[kind], k, 321 * k), (kind, out)
+            assert out.n_lines == 4 * n_rec - (1 if kind == "len" else 0) and not out.finished
+            assert p["retried"] and not p["exact"], p
+            assert err_ms < 2.0 * clean_ms + 0.6, (kind, hist, err_ms, clean_ms)
+            if hist:
+                ores, ost = oracle.each_stats(oracle.synth_fixed_records(2000, first=k - 2000).tobytes(), 150)
+                assert st.n_records == k and int(st.qual_hist.sum()) == 150 * k
+                got = idx[4 * (k - 1):4 * k].cpu().numpy().view(np.uint32)
+                assert int(got[3]) == (321 * k - 1) & 0xFFFFFFFF
+            t[off:off + 1] = saved
+    # small inputs, every byte position of a bad '@' in a 40-record file: same result as the oracle
+    base = oracle.synth_fixed_records(40).tobytes()
+    for k in range(0, 40, 3):
+        data = bytearray(base)
+        data[321 * k] = ord("#")
+        check_device_vs_oracle(torch, oracle, eng, bytes(data))
+
+
 def test_count_mode_varying_shapes(torch, oracle, eng):
     data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
     check_count_mode(torch, oracle, eng, data)
