@@ -32,45 +32,60 @@ namespace {
 // coordinates).  If two or more kinds vary, the launch goes to the speculative kernel's variable-length
 // variant -- and so does a shard whose head holds bytes >= 0x80.  A hint only: either variant delivers the
 // exact result on any input.
-constexpr int PROBE_BYTES = 8192, PROBE_LINES = 256;
-__global__ void __launch_bounds__(32) fq_init_kernel(DevResult* r, int spec_fail, int line_phase, const uint8_t* data,
-                                                     unsigned long long n, int probe)
+constexpr int PROBE_BYTES = 8192, PROBE_LINES = 256, PROBE_THREADS = 512;
+__global__ void __launch_bounds__(PROBE_THREADS) fq_init_kernel(DevResult* r, int spec_fail, int line_phase, const uint8_t* data,
+                                                                unsigned long long n, int probe)
 {
     __shared__ unsigned short pos[PROBE_LINES + 1];
-    const int lane = threadIdx.x;
+    __shared__ unsigned int warp_cnt[PROBE_THREADS / 32];
+    __shared__ unsigned int s_varies, s_hi;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     int shape_var = 0;
     if (probe && n >= (unsigned long long)PROBE_BYTES) {
-        // newline positions of the first PROBE_BYTES, in order: 256 bytes per lane, warp prefix of the counts
-        const uint8_t* d = data + lane * (PROBE_BYTES / 32);
-        int c = 0;
-        unsigned hi = 0;
-        for (int i = 0; i < PROBE_BYTES / 32; ++i) {
-            c += d[i] == '\n';
-            hi |= d[i];
+        // newline positions of the first PROBE_BYTES, in order: 16 bytes per thread, block prefix of the counts
+        if (t == 0) {
+            s_varies = 0;
+            s_hi = 0;
         }
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(data) + t);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        unsigned m = 0;                                          // bit i: byte i of the piece is '\n'
+        for (int i = 0; i < 16; ++i) m |= (((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) == '\n' ? 1u : 0u) << i;
+        const unsigned hi = (v.x | v.y | v.z | v.w) & 0x80808080u;
+        const int c = __popc(m);
         int incl = c;
         for (int k = 1; k < 32; k <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, k);
-            if (lane >= k) incl += v;
+            const int u = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += u;
         }
-        int rank = incl - c;
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int i = 0; i < PROBE_BYTES / 32 && rank < PROBE_LINES; ++i)
-            if (d[i] == '\n') pos[rank++] = (unsigned short)(lane * (PROBE_BYTES / 32) + i);
-        __syncwarp();
+        if (lane == 31) warp_cnt[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < PROBE_THREADS / 32; ++k) {
+            if (k < warp) before += warp_cnt[k];
+            total += warp_cnt[k];
+        }
+        int rank = before + incl - c;
+        while (m && rank < PROBE_LINES) {
+            pos[rank++] = (unsigned short)(16 * t + __ffs(m) - 1);
+            m &= m - 1;
+        }
+        if (hi) atomicOr(&s_hi, 1u);
+        __syncthreads();
         const int nl = total < PROBE_LINES ? total : PROBE_LINES;
         // line j = (pos[j], pos[j + 1]]; compare the lengths of line j and line j + 4
         unsigned varies = 0;                                     // bit k: some line of kind k changed its length
-        for (int j = lane; j + 5 < nl; j += 32)
+        for (int j = t; j + 5 < nl; j += PROBE_THREADS)
             if (pos[j + 1] - pos[j] != pos[j + 5] - pos[j + 4]) varies |= 1u << (j & 3);
-        varies = __reduce_or_sync(0xffffffffu, varies);
-        shape_var = (nl >= 16 && __popc(varies) >= 2) ? 1 : 0;
+        if (varies) atomicOr(&s_varies, varies);
+        __syncthreads();
+        shape_var = (nl >= 16 && __popc(s_varies) >= 2) ? 1 : 0;
         // bytes >= 0x80 (UTF-8 in the id lines, say): the predicting variant leaves the fast path at the first
         // window it has to scan that holds one; the variable-length variant only minds them in the sequence and
         // quality lines themselves
-        if (__any_sync(0xffffffffu, (hi & 0x80u) != 0)) shape_var = 1;
+        if (s_hi) shape_var = 1;
     }
-    if (lane != 0) return;
+    if (t != 0) return;
     r->shape_var = shape_var;
     r->first_bad = NONE64;
     r->tail_start = NONE64;
@@ -505,7 +520,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.trace = ctx->d_trace;
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
-    fq_init_kernel<<<1, 32, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3), sh->d_bytes, sh->n_avail,
+    fq_init_kernel<<<1, PROBE_THREADS, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3), sh->d_bytes, sh->n_avail,
                                      (fast && (sh->flags & FQB_F_HIST) && !getenv("FQB_NO_VAR")) ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8, st));   // block + outcome slots

@@ -168,17 +168,25 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long* base = p.stats + stats_base_off(P);
     if (!skip) {
-        for (size_t pos = i0; pos < P; pos += stride) {
+        // one warp per position: the 256 raw counters of the row are summed by the lanes (8 each)
+        const int lane = threadIdx.x & 31;
+        const size_t wstride = stride / 32;
+        for (size_t pos = i0 / 32; pos < P; pos += wstride) {
             const unsigned long long* row = p.seqraw + pos * 256;
             unsigned long long all = 0;
-            for (int b = 0; b < 256; ++b) all += row[b];
-            const unsigned long long a = row['A'], c = row['C'], g = row['G'], t = row['T'], n = row['N'];
-            base[pos * 6 + 0] = a;
-            base[pos * 6 + 1] = c;
-            base[pos * 6 + 2] = g;
-            base[pos * 6 + 3] = t;
-            base[pos * 6 + 4] = n;
-            base[pos * 6 + 5] = all - a - c - g - t - n;
+            for (int b = lane; b < 256; b += 32) all += row[b];
+            all = warp_sum_u64(all);
+            if (lane == 0) {
+                const unsigned long long a = row['A'], c = row['C'], g = row['G'], t = row['T'], n = row['N'];
+                base[pos * 6 + 0] = a;
+                base[pos * 6 + 1] = c;
+                base[pos * 6 + 2] = g;
+                base[pos * 6 + 3] = t;
+                base[pos * 6 + 4] = n;
+                base[pos * 6 + 5] = all - a - c - g - t - n;
+                if (total)   // (streaming: the chunk's base classes into the running totals, by the lane that made them)
+                    for (int k = 0; k < 6; ++k) total[stats_base_off(P) + pos * 6 + k] += base[pos * 6 + k];
+            }
         }
     }
     // grid-wide ordering is not needed: totals only read words this thread itself finalized or
@@ -186,11 +194,9 @@ __global__ void fq_finalize_kernel(const ScanParams p, DevCarry* carry, unsigned
     if (total && !skip) {
         const size_t nb = stats_base_off(P), nq = stats_qual_off(P), nw = stats_words(P);
         for (size_t i = i0; i < nw; i += stride) {
-            if (i >= nb && i < nq) continue;  // base_hist: added by the owning thread below
+            if (i >= nb && i < nq) continue;  // base_hist: added above, by the lane that folded the row
             total[i] += p.stats[i];
         }
-        for (size_t pos = i0; pos < P; pos += stride)
-            for (int k = 0; k < 6; ++k) total[nb + pos * 6 + k] += base[pos * 6 + k];
     }
     if (i0 == 0) {
         DevResult* r = p.res;
