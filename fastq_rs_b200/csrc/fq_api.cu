@@ -463,7 +463,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     // ends in its own share of a staging area sized for lines of >= 16 bytes on average (a range that
     // needs more gives up and the exact path writes the index)
     const bool fast = ctx->nchunk <= 10 && !getenv("FQB_NO_FAST");
-    uint64_t srange_bytes, stage_share = 0, n_sranges;
+    uint64_t srange_bytes, stage_share = 0, n_sranges, desc_cap = 0;
     {
         // equal ranges, rounded DOWN to 16 bytes; the last range takes the remainder (a little more work
         // for one warp, but a range too short to hold a few records could not infer its start)
@@ -475,8 +475,11 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
         if (fast && want_index) {
             // (lines of >= 16 bytes on average; the last range is longer by the remainder)
             const uint64_t rem = sh->n_own > live * srange_bytes ? sh->n_own - live * srange_bytes : 0;
-            stage_share = (srange_bytes + rem) / 16 + 64;
-            const uint64_t need = live * stage_share;
+            stage_share = ((srange_bytes + rem) / 16 + 64 + 3) / 4 * 4;   // (a multiple of 4: the descriptors behind are uint4)
+            // window descriptors (4 words each): one per window; a window that consumes less than 256 bytes on
+            // average (records of a few bytes) overflows them -- the exact path writes the index then
+            desc_cap = (srange_bytes + rem) / 256 + 64;
+            const uint64_t need = live * (stage_share + 4 * desc_cap);
             if (need > ctx->index_stage_cap) {
                 if (ctx->d_index_stage) {
                     // (an earlier parse of this context may still be using the staging area on ANOTHER stream)
@@ -508,6 +511,8 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     p.ranges = ctx->d_ranges;
     p.nranges = (uint32_t)ctx->grid;
     p.index_stage = ctx->d_index_stage;
+    p.desc = ctx->d_index_stage ? ctx->d_index_stage + n_sranges * stage_share : nullptr;
+    p.desc_cap = desc_cap;
     p.sranges = ctx->d_sranges;
     p.srange_bytes = srange_bytes;
     p.n_sranges = (uint32_t)n_sranges;

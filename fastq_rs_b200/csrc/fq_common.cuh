@@ -74,9 +74,10 @@ struct StreamRange {
     unsigned long long end;         // cursor after the last such record = start of the first one beyond the range
     unsigned long long n_lines;     // '\n' of those records inside the owned bytes (+ the ones in front of range 0's first record)
     unsigned long long rank0;       // prefix of n_lines (fq_stream_verify_kernel): where the staged line ends go
-    uint32_t flags;                 // 1 = delivered, 2 = gave up
-    uint32_t pad;
+    uint32_t flags;                 // 1 = delivered, 2 = gave up, 3 = stopped at a bad record (F_CAN_RETRY)
+    uint32_t n_desc;                // window descriptors the range wrote (DESC_RAW_ONLY: none, its line ends are all staged)
 };
+constexpr uint32_t DESC_RAW_ONLY = 0xFFFFFFFFu;
 
 // streaming carry block (device resident, lives across chunk launches)
 struct DevCarry {
@@ -106,6 +107,14 @@ struct ScanParams {
     unsigned long long srange_bytes;
     uint32_t* index_stage;          // speculative kernel: range r stages its line ends at index_stage + r * stage_share
     unsigned long long stage_share;
+    // ... or, window by window, DESCRIBES them: a window of predicted records is an arithmetic sequence -- 16 bytes
+    // instead of 16 bytes per record.  desc + 4 * (r * desc_cap + k) = the k-th window of range r:
+    //   [0] line ends of the window | kind << 24   kind 0: they are staged at index_stage + r * stage_share + [1]
+    //   [1] kind 1: low 32 bits of the stream offset of the window's first record
+    //   [2] kind 1: offsets of the 1st | 2nd << 16 line end within a record    [3] 3rd | record length << 16
+    // fq_stream_compact_kernel turns descriptors (and staged runs) into the dense index.
+    uint32_t* desc;
+    unsigned long long desc_cap;
     uint32_t* index;
     unsigned long long index_cap;
     DevResult* res;

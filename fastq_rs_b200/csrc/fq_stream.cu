@@ -751,6 +751,16 @@ __device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t 
     return __reduce_add_sync(0xffffffffu, cnt);
 }
 
+// one window descriptor of range rid (see ScanParams::desc); false if the range's share is full
+__device__ __forceinline__ bool desc_put(const ScanParams& p, uint32_t rid, uint32_t& dcount, int lane, uint32_t w0,
+                                         uint32_t w1, uint32_t w2, uint32_t w3)
+{
+    if (dcount >= p.desc_cap) return false;
+    if (lane < 4) p.desc[((size_t)rid * p.desc_cap + dcount) * 4 + lane] = lane == 0 ? w0 : lane == 1 ? w1 : lane == 2 ? w2 : w3;
+    ++dcount;
+    return true;
+}
+
 struct StreamCta {
     uint32_t n_records, n_bases;   // totals of the CTA (u32: a CTA sees < 4 G bases per launch; native shared atomics)
     uint32_t recs;          // records consumed by the CTA (drives the drain of the u16 counter halves)
@@ -996,6 +1006,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     unsigned long long cur = 0, lrank = 0;
     bool failed = false;
     uint32_t my_epoch = 0;
+    uint32_t dcount = 0;            // window descriptors written (the predicting variant; see ScanParams::desc)
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
@@ -1035,6 +1046,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     }
                     failed = __any_sync(0xffffffffu, failed);
                     if (K && (unsigned long long)(w.src + (long long)list[c] - 1) >= p.n_own) failed = true;   // (a shard inside one record)
+                    if (!VAR && want_index && K && !desc_put(p, rid, dcount, lane, K, 0u, 0u, 0u)) failed = true;
                     lrank = K;
                     if (lane == 0) p.res->line_phase = (int)((4u - K) & 3u);
                 }
@@ -1113,13 +1125,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 n_lines = 4u * n_rec;
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share) {
-                        failed = true;   // staging share too small: the exact path writes the index
+                    // the line ends of a predicted window are an arithmetic sequence: 16 bytes describe them
+                    const uint32_t o2 = sh.Lh + sh.Lsq;
+                    if (!desc_put(p, rid, dcount, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad,
+                                  (sh.Lh - 1u) | ((o2 - 1u) << 16), (o2 + sh.Lp - 1u) | (sh.reclen << 16))) {
+                        failed = true;   // descriptor share too small: the exact path writes the index
                         break;
                     }
-                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + idx_le;
-                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
-                    for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
                 }
             } else if (can_predict) {
                 // records that start inside the range
@@ -1155,14 +1167,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 n_lines = 4u * n_rec;
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share) {
-                        failed = true;   // staging share too small: the exact path writes the index
+                    // the line ends of a predicted window are an arithmetic sequence: 16 bytes describe them
+                    const uint32_t o2 = sh.Lh + sh.Lsq;
+                    if (!desc_put(p, rid, dcount, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad,
+                                  (sh.Lh - 1u) | ((o2 - 1u) << 16), (o2 + sh.Lp - 1u) | (sh.reclen << 16))) {
+                        failed = true;   // descriptor share too small: the exact path writes the index
                         break;
                     }
-                    // lane = 4 * (record mod 8) + line: the line-end offset is fixed per lane
-                    uint32_t v = (uint32_t)(p.stream_offset + w.src) + w.pad + ((uint32_t)lane >> 2) * sh.reclen + idx_le;
-                    uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
-                    for (uint32_t j = lane; j < n_lines; j += 32, v += 8u * sh.reclen) out[j] = v;
                 }
             } else if (HIST && predict && flex && full) {
                 // ---- predicted window, header lengths vary: find every header end ('\n' search over the 128
@@ -1221,7 +1232,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 31u);
                 next = n_rec == n_fit2 ? s : nxt;
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share) {
+                    if (lrank + n_lines > p.stage_share || !desc_put(p, rid, dcount, lane, n_lines, (uint32_t)lrank, 0u, 0u)) {
                         failed = true;
                         break;
                     }
@@ -1339,7 +1350,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
                 }
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share) {
+                    if (lrank + n_lines > p.stage_share || !desc_put(p, rid, dcount, lane, n_lines, (uint32_t)lrank, 0u, 0u)) {
                         failed = true;   // staging share too small: the exact path writes the index
                         break;
                     }
@@ -1379,6 +1390,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             sr.end = cur;
             sr.n_lines = lrank;
             sr.flags = failed ? 2u : (stopped ? 3u : 1u);
+            // (no window predicted: every line end of the range is staged, back to back -- one plain copy)
+            sr.n_desc = (VAR || dbg_pred == 0) ? DESC_RAW_ONLY : dcount;
             atomicAdd(&p.res->n_win_pred, (unsigned long long)dbg_pred);
             atomicAdd(&p.res->n_win_scan, (unsigned long long)dbg_scan);
             if (failed) atomicExch(&p.res->spec_fail, 1);
@@ -1478,30 +1491,110 @@ __global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams
     }
 }
 
-// move the staged line ends of every range to their place in the caller's index (only when the
-// speculative launch stands; the exact kernel writes the index directly)
+// the line ends of every range to their place in the caller's index (only when the speculative launch stands;
+// the exact kernel writes the index directly): staged runs are copied, window descriptors expanded
 __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams p, const DevCarry* carry)
 {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint4 d_first;
     if (p.res->spec_fail) return;
     if (carry && carry->status != 0) return;
     const uint32_t nlive = p.n_sranges;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (uint32_t r = blockIdx.x; r < nlive; r += gridDim.x) {
         const StreamRange sr = p.sranges[r];
         const uint32_t* src = p.index_stage + (size_t)r * p.stage_share;
-        // (source and destination are shifted against each other by an arbitrary number of entries,
-        // so this stays a 4-byte copy; four loads in flight per thread keep the memory system busy)
         const unsigned long long n = min(sr.n_lines, p.index_cap > sr.rank0 ? p.index_cap - sr.rank0 : 0ull);
         uint32_t* dst = p.index + sr.rank0;
-        unsigned long long i = threadIdx.x;
-        for (; i + 3ull * blockDim.x < n; i += 4ull * blockDim.x) {
-            const uint32_t a = __ldg(src + i), b = __ldg(src + i + blockDim.x), c = __ldg(src + i + 2 * blockDim.x),
-                           d = __ldg(src + i + 3 * blockDim.x);
-            dst[i] = a;
-            dst[i + blockDim.x] = b;
-            dst[i + 2 * blockDim.x] = c;
-            dst[i + 3 * blockDim.x] = d;
+        if (sr.n_desc == DESC_RAW_ONLY) {
+            // (source and destination are shifted against each other by an arbitrary number of entries,
+            // so this stays a 4-byte copy; four loads in flight per thread keep the memory system busy)
+            unsigned long long i = t;
+            for (; i + 3ull * blockDim.x < n; i += 4ull * blockDim.x) {
+                const uint32_t a = __ldg(src + i), b = __ldg(src + i + blockDim.x), c = __ldg(src + i + 2 * blockDim.x),
+                               d = __ldg(src + i + 3 * blockDim.x);
+                dst[i] = a;
+                dst[i + blockDim.x] = b;
+                dst[i + 2 * blockDim.x] = c;
+                dst[i + 3 * blockDim.x] = d;
+            }
+            for (; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+            continue;
         }
-        for (; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+        // window descriptors, 256 at a time: block prefix of their line counts, then every warp expands its 32
+        const uint4* D = reinterpret_cast<const uint4*>(p.desc) + (size_t)r * p.desc_cap;
+        unsigned long long base = 0;
+        for (uint32_t c0 = 0; c0 < sr.n_desc; c0 += 256u) {
+            const uint4 d = c0 + t < sr.n_desc ? __ldg(D + c0 + t) : make_uint4(0, 0, 0, 0);
+            const uint32_t nl = d.x & 0xFFFFFFu;
+            uint32_t incl = nl;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, k);
+                if (lane >= k) incl += v;
+            }
+            __syncthreads();                        // (warp_tot of the previous round has been read)
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                before += k < warp ? warp_tot[k] : 0u;
+                total += warp_tot[k];
+            }
+            const unsigned long long my_off = base + before + incl - nl;
+            const uint32_t k4 = (uint32_t)lane & 3u;
+            // The usual case on fixed-length reads: the 256 windows continue one another -- same record shape, each
+            // starting where the one before ended -- so the whole round is ONE arithmetic sequence and every thread
+            // writes every 256th entry of it (coalesced, no shuffles).
+            if (t == 0) d_first = d;
+            __syncthreads();
+            {
+                const uint4 f = d_first;
+                const uint32_t reclen = f.w >> 16;
+                const bool pad = c0 + t >= sr.n_desc;
+                const bool cont = pad || ((d.x >> 24) == 1u && d.z == f.z && d.w == f.w &&
+                                          d.y == f.y + (uint32_t)((my_off - base) >> 2) * reclen);
+                // ... or, on reads of varying length, 256 scanned windows whose staged line ends lie back to back
+                const bool raw_run = pad || ((d.x >> 24) == 0u && d.y == f.y + (uint32_t)(my_off - base));
+                const bool all_cont = __syncthreads_and(cont), all_raw = __syncthreads_and(raw_run);
+                if (all_raw && (f.x >> 24) == 0u) {
+                    const uint32_t* s0 = src + f.y;
+                    for (uint32_t e = t; e < total; e += 256u)
+                        if (base + e < n) dst[base + e] = __ldg(s0 + e);
+                    base += total;
+                    continue;
+                }
+                if (all_cont && (f.x >> 24) == 1u) {
+                    const uint32_t le = k4 == 0 ? (f.z & 0xFFFFu) : k4 == 1 ? (f.z >> 16) : k4 == 2 ? (f.w & 0xFFFFu) : reclen - 1u;
+                    uint32_t v = f.y + ((uint32_t)t >> 2) * reclen + le;
+                    for (uint32_t e = t; e < total; e += 256u, v += 64u * reclen)
+                        if (base + e < n) dst[base + e] = v;
+                    base += total;
+                    continue;
+                }
+            }
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t w0 = __shfl_sync(0xffffffffu, d.x, i);
+                const uint32_t n_i = w0 & 0xFFFFFFu;
+                if (n_i == 0) continue;
+                const uint32_t w1 = __shfl_sync(0xffffffffu, d.y, i), w2 = __shfl_sync(0xffffffffu, d.z, i),
+                               w3 = __shfl_sync(0xffffffffu, d.w, i);
+                const unsigned long long o_i = __shfl_sync(0xffffffffu, my_off, i);
+                if (w0 >> 24) {
+                    // predicted records: entry j = first record + (j / 4) * record length + offset of line end j % 4
+                    const uint32_t reclen = w3 >> 16;
+                    const uint32_t le = k4 == 0 ? (w2 & 0xFFFFu) : k4 == 1 ? (w2 >> 16) : k4 == 2 ? (w3 & 0xFFFFu) : reclen - 1u;
+                    uint32_t v = w1 + ((uint32_t)lane >> 2) * reclen + le;
+                    for (uint32_t j = lane; j < n_i; j += 32, v += 8u * reclen)
+                        if (o_i + j < n) dst[o_i + j] = v;
+                } else {
+                    for (uint32_t j = lane; j < n_i; j += 32)
+                        if (o_i + j < n) dst[o_i + j] = __ldg(src + w1 + j);
+                }
+            }
+            base += total;
+        }
     }
 }
 
