@@ -238,19 +238,23 @@ def time_config(eng, torch, steps, warmup, parse, n_bytes, n_rec, peak, index_en
     assert out.status == 0 and out.n_records == n_rec, out
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k = []
+    k, ki = [], []
     e0.record()
     for _ in range(steps):
         parse()
         eng.fetch()
         k.append(eng.last_scan_ms())
+        ki.append(eng.last_index_ms())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    k_ms = float(np.mean(k))
+    k_ms, i_ms = float(np.mean(k)), float(np.mean(ki))
     alg = n_bytes + 4 * index_entries
-    return {"value": n_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "kernel_ms": k_ms,
-            "algorithmic_bytes": alg, "roofline_frac": alg / (k_ms * 1e-3) / 1e9 / peak, "records": n_rec}
+    # the scan kernel reads every byte; the dense index (16 B / record) is written by the index kernel behind it
+    # from the scan kernel's window descriptors: the algorithmic bytes are charged to the two together
+    return {"value": n_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "kernel_ms": k_ms, "index_kernel_ms": i_ms,
+            "algorithmic_bytes": alg, "roofline_frac": alg / ((k_ms + i_ms) * 1e-3) / 1e9 / peak,
+            "scan_kernel_frac": n_bytes / (k_ms * 1e-3) / 1e9 / peak, "records": n_rec}
 
 
 def run_ours(args):
@@ -313,7 +317,7 @@ def run_ours(args):
     # ---- timed region: HBM-resident ---------------------------------------------------------
     launches0 = eng.launch_count()
     coll0 = sp.collectives
-    scan_ms = []
+    scan_ms, index_ms = [], []
     with ClockSampler(local) as clk:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,6 +325,7 @@ def run_ours(args):
         for _ in range(args.steps):
             step()
             scan_ms.append(eng.last_scan_ms())
+            index_ms.append(eng.last_index_ms())
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -332,15 +337,24 @@ def run_ours(args):
     value = total / (ms_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel, live CUDA events on its stream ----------------------
-    k_ms = float(np.mean(scan_ms))
+    k_ms, i_ms = float(np.mean(scan_ms)), float(np.mean(index_ms))
     alg_bytes = n_own + 16 * (n_own // REC_BYTES)            # 1 B read per input byte + 16 B index per record
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    # The scan kernel (fq_stream_kernel) reads every input byte and leaves 16-byte window descriptors; the dense
+    # 16 B / record index is written by the index kernel right behind it (fq_stream_compact_kernel).  The
+    # algorithmic bytes of the step are charged to the two kernels TOGETHER; `scan_kernel` below has the scan
+    # kernel alone against the bytes it moves itself (the input).
+    achieved = alg_bytes / ((k_ms + i_ms) * 1e-3) / 1e9
     traffic, traffic_src = profiled_traffic(args.gib)
-    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5,32,4096>, HIST, predicting variant>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5,32,4096>, HIST, predicting variant> + fq_stream_compact_kernel (index)",
+                "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": args.traffic_bytes if args.traffic_bytes is not None else traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes}
+                "kernel_ms": k_ms + i_ms, "algorithmic_bytes": alg_bytes,
+                "kernels": {"fq_stream_kernel": {"ms": k_ms, "bytes": n_own, "GBps": n_own / (k_ms * 1e-3) / 1e9,
+                                                 "frac": n_own / (k_ms * 1e-3) / 1e9 / peak},
+                            "fq_stream_compact_kernel": {"ms": i_ms, "bytes": 16 * (n_own // REC_BYTES),
+                                                         "GBps": 16 * (n_own // REC_BYTES) / (max(i_ms, 1e-9) * 1e-3) / 1e9}}}
 
     # ---- every BASELINE configuration, one GPU each (N = 1 line only) --------------------------
     configs = None

@@ -28,7 +28,7 @@ SYMBOLS = [
     "fqb_abi_version", "fqb_stats_words", "fqb_stats_len_hist_off", "fqb_stats_base_hist_off",
     "fqb_stats_qual_hist_off", "fqb_create", "fqb_destroy", "fqb_strerror", "fqb_last_error",
     "fqb_parse_device", "fqb_count_lines_device", "fqb_fetch_line_count", "fqb_fetch",
-    "fqb_device_stats", "fqb_device_result", "fqb_launch_count", "fqb_last_scan_ms", "fqb_parse_host",
+    "fqb_device_stats", "fqb_device_result", "fqb_launch_count", "fqb_last_scan_ms", "fqb_last_index_ms", "fqb_parse_host",
     "fqb_stream_begin", "fqb_stream_acquire", "fqb_stream_submit", "fqb_stream_finish",
     "fqb_host_alloc", "fqb_host_free", "fqb_synth_fixed_device", "fqb_synth_var_device",
     "fqb_synth_var_sizes_device", "fqb_filter_device", "fqb_fetch_filter", "fqb_last_path",
@@ -116,6 +116,8 @@ def lib():
     L.fqb_device_result.restype = vp
     L.fqb_launch_count.argtypes = [vp]
     L.fqb_launch_count.restype = u64
+    L.fqb_last_index_ms.argtypes = [vp]
+    L.fqb_last_index_ms.restype = C.c_float
     L.fqb_last_scan_ms.argtypes = [vp]
     L.fqb_last_scan_ms.restype = C.c_float
     L.fqb_parse_host.argtypes = [vp, vp, u64, u64, u32, C.POINTER(Result), vp, vp, u64, C.POINTER(u64)]

@@ -222,8 +222,8 @@ struct fqb_ctx {
     unsigned long long* h_fres = nullptr;    // pinned [4]
     DevResult* h_res = nullptr;  // pinned
     unsigned long long* h_linecount = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // scan kernel; index compaction
+    bool ev_valid = false, ev_index_valid = false;
     uint64_t launches = 0;
     unsigned long long* d_trace = nullptr;  // FQB_TRACE=<file>: kernel timeline, dumped by fqb_fetch
     std::string trace_path;
@@ -380,6 +380,8 @@ int fqb_create(const fqb_config* cfg, fqb_ctx** out)
     }
     CKC(cudaEventCreate(&ctx->ev0));
     CKC(cudaEventCreate(&ctx->ev1));
+    CKC(cudaEventCreate(&ctx->ev2));
+    CKC(cudaEventCreate(&ctx->ev3));
 #undef CKC
     *out = ctx;
     return FQB_OK;
@@ -439,6 +441,8 @@ void fqb_destroy(fqb_ctx* ctx)
     if (ctx->h_carry) cudaFreeHost(ctx->h_carry);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     delete ctx;
 }
 
@@ -467,7 +471,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     {
         // equal ranges, rounded DOWN to 16 bytes; the last range takes the remainder (a little more work
         // for one warp, but a range too short to hold a few records could not infer its start)
-        const uint64_t nr = (uint64_t)ctx->grid * stream_warps(ctx->nchunk);
+        const uint64_t nr = (uint64_t)ctx->grid * stream_warps(ctx->nchunk, (sh->flags & FQB_F_HIST) != 0);
         srange_bytes = sh->n_own / nr / 16 * 16;
         if (srange_bytes < 8192) srange_bytes = 8192;
         const uint64_t live = std::max<uint64_t>(1, std::min<uint64_t>(nr, sh->n_own / srange_bytes));
@@ -560,8 +564,14 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             ctx->launches += 7;
         }
         if (timed) ctx->ev_valid = fast || !(p.flags & F_INFER_START);
+        if (timed) ctx->ev_index_valid = false;
         if (fast && want_index) {
+            if (timed) CK(cudaEventRecord(ctx->ev2, st));
             CK(launch_stream_compact(p, carry, ctx->grid, st));
+            if (timed) {
+                CK(cudaEventRecord(ctx->ev3, st));
+                ctx->ev_index_valid = true;
+            }
             ctx->launches += 1;
         }
         if (fast && (p.flags & F_EOF) && !(p.flags & F_INFER_START)) {
@@ -660,6 +670,15 @@ float fqb_last_scan_ms(fqb_ctx* ctx)
     if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.f;
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+float fqb_last_index_ms(fqb_ctx* ctx)
+{
+    if (!ctx || !ctx->ev_index_valid) return 0.f;
+    if (cudaEventSynchronize(ctx->ev3) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) != cudaSuccess) return -1.f;
     return ms;
 }
 

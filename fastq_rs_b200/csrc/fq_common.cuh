@@ -158,7 +158,7 @@ cudaError_t launch_diagnose(const ScanParams& p, DevCarry* carry, cudaStream_t s
 cudaError_t launch_rerun_reset(const ScanParams& p, int mode, cudaStream_t st);
 cudaError_t launch_range_count(const ScanParams& p, DevCarry* carry, int nranges, unsigned long long range_bytes,
                                cudaStream_t st);
-int stream_warps(int nchunk);
+int stream_warps(int nchunk, bool hist);
 cudaError_t stream_configure();
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st);
 cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStream_t st);

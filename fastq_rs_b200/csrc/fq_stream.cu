@@ -1070,6 +1070,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         unsigned long long tail_x = NONE64;
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
+        uint32_t acc_rec = 0;   // records of predicted windows not yet in the CTA's totals
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
         if (VAR) {
             // ---- reads of varying length: every window is scanned (var_loop) ---------------------------
@@ -1121,7 +1122,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 ++dbg_pred;
                 n_rec = n_fit;                                                // records that start inside the range
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
-                if (lane == 0) atomicAdd(&cta.n_records, n_rec);
+                acc_rec += n_rec;    // (into the CTA's totals when the shape changes or the range ends)
                 n_lines = 4u * n_rec;
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
@@ -1159,11 +1160,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 }
                 ++dbg_pred;
                 if (n_rec == 0) continue;
-                if (lane == 0) {
-                    atomicAdd(&cta.n_records, n_rec);
-                    atomicAdd(&cta.n_bases, n_rec * Ls);
-                    atomicAdd(lenh + Ls, n_rec);
-                }
+                acc_rec += n_rec;    // records of the current shape: counted when it changes or the range ends
                 n_lines = 4u * n_rec;
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
@@ -1223,11 +1220,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 }
                 ++dbg_pred;
                 if (n_rec == 0) continue;
-                if (lane == 0) {
-                    atomicAdd(&cta.n_records, n_rec);
-                    atomicAdd(&cta.n_bases, n_rec * Ls);
-                    atomicAdd(lenh + Ls, n_rec);
-                }
+                acc_rec += n_rec;    // records of the current shape: counted when it changes or the range ends
                 n_lines = 4u * n_rec;
                 const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 31u);
                 next = n_rec == n_fit2 ? s : nxt;
@@ -1246,6 +1239,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             } else {
                 // ---- scanned window -------------------------------------------------------------------
                 ++dbg_scan;
+                // the records predicted so far go into the CTA's totals before the shape they were counted with changes
+                if (acc_rec) {
+                    if (lane == 0) {
+                        atomicAdd(&cta.n_records, acc_rec);
+                        if (HIST) {
+                            const uint32_t Ls = sh.Lsq - 1u - sh.cr_s;
+                            atomicAdd(&cta.n_bases, acc_rec * Ls);
+                            atomicAdd(lenh + Ls, acc_rec);
+                        }
+                    }
+                    acc_rec = 0;
+                }
                 uint32_t hib;
                 const uint32_t total = win_scan<C, HIST>(buf_s, list, w, hib, lane, lt_mask);
                 const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
@@ -1364,6 +1369,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             cur = w.src + next;
             if (tail_x != NONE64) break;
             if (HIST) drain_tick<C>(hist, p, cta, n_rec, my_epoch, warp, lane);   // u16 counter halves
+        }
+        if (!VAR && acc_rec && lane == 0) {                       // (see the scanned branch)
+            atomicAdd(&cta.n_records, acc_rec);
+            if (HIST) {
+                const uint32_t Ls = sh.Lsq - 1u - sh.cr_s;
+                atomicAdd(&cta.n_bases, acc_rec * Ls);
+                atomicAdd(lenh + Ls, acc_rec);
+            }
         }
         bool stopped = false;
         if (tail_x != NONE64 && !failed) {
@@ -1601,21 +1614,22 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-using SCfg5 = SCfg<5, 32, 4096>;     // P <= 160: 80 KB of counters, 32 warps x 4 KiB windows
+using SCfg5 = SCfg<5, 32, 4096>;     // P <= 160, no histograms: 32 warps x 4 KiB windows (bandwidth- and latency-bound: warps help)
+using SCfg5H = SCfg<5, 28, 4096>;    // P <= 160 with histograms: 80 KB of counters, 28 warps x 4 KiB windows -- the rounds are
+                                     // issue-bound and want registers: 72 per thread (no spills) beat 32 warps at 64 (+1 %)
 using SCfg10 = SCfg<10, 22, 2560>;   // P <= 320: 160 KB of counters, 22 warps x 2.5 KiB windows (measured best of
                                      // 16 x 3584 / 22 x 2560 / 26 x 2048 on fixed 300 bp and on 50..300 bp reads)
-
 // the variable-length variants: same ranges (the host cuts the shard into grid x NWARPS of them), a spare row per chunk
-using VCfg5 = SCfg<5, 32, 4096, 1>;
+using VCfg5 = SCfg<5, 28, 4096, 1>;
 using VCfg10 = SCfg<10, 22, 4096, 1, 32>;   // rows 32 .. 127 only: 124 KB of counters leave room for 4 KiB windows
-static_assert(VCfg5::NWARPS == SCfg5::NWARPS && VCfg10::NWARPS == SCfg10::NWARPS, "both variants walk the same ranges");
+static_assert(VCfg5::NWARPS == SCfg5H::NWARPS && VCfg10::NWARPS == SCfg10::NWARPS, "both variants walk the same ranges");
 
-int stream_warps(int nchunk) { return nchunk <= 5 ? SCfg5::NWARPS : SCfg10::NWARPS; }
+int stream_warps(int nchunk, bool hist) { return nchunk <= 5 ? (hist ? SCfg5H::NWARPS : SCfg5::NWARPS) : SCfg10::NWARPS; }
 
-template <class C, class V>
+template <class C, class H, class V>
 static cudaError_t configure_set()
 {
-    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H::TOTAL);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(fq_stream_kernel<V, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V::TOTAL);
     if (e != cudaSuccess) return e;
@@ -1624,17 +1638,17 @@ static cudaError_t configure_set()
 
 cudaError_t stream_configure()
 {
-    cudaError_t e = configure_set<SCfg5, VCfg5>();
+    cudaError_t e = configure_set<SCfg5, SCfg5H, VCfg5>();
     if (e != cudaSuccess) return e;
-    return configure_set<SCfg10, VCfg10>();
+    return configure_set<SCfg10, SCfg10, VCfg10>();
 }
 
-template <class C, class V>
+template <class C, class H, class V>
 static void launch_set(const ScanParams& p, int grid, cudaStream_t st)
 {
     if (p.flags & F_HIST) {
         // (one of the two returns at once: res->shape_var, set by fq_init_kernel's look at the head of the shard)
-        fq_stream_kernel<C, true, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+        fq_stream_kernel<H, true, false><<<grid, H::NTHREADS, H::TOTAL, st>>>(p);
         fq_stream_kernel<V, true, true><<<grid, V::NTHREADS, V::TOTAL, st>>>(p);
     } else {
         fq_stream_kernel<C, false, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
@@ -1644,9 +1658,9 @@ static void launch_set(const ScanParams& p, int grid, cudaStream_t st)
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st)
 {
     if (nchunk <= 5)
-        launch_set<SCfg5, VCfg5>(p, grid, st);
+        launch_set<SCfg5, SCfg5H, VCfg5>(p, grid, st);
     else
-        launch_set<SCfg10, VCfg10>(p, grid, st);
+        launch_set<SCfg10, SCfg10, VCfg10>(p, grid, st);
     return cudaGetLastError();
 }
 

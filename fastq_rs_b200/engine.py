@@ -244,6 +244,9 @@ class Engine:
     def last_scan_ms(self) -> float:
         return float(self.L.fqb_last_scan_ms(self.ctx))
 
+    def last_index_ms(self) -> float:
+        return float(self.L.fqb_last_index_ms(self.ctx))
+
     def launch_count(self) -> int:
         return int(self.L.fqb_launch_count(self.ctx))
 

@@ -181,6 +181,9 @@ uint64_t fqb_launch_count(fqb_ctx *ctx);
 /* CUDA-event time of the main scan kernel of the last fqb_parse_device call, in ms
  * (waits for it); <0 on error */
 float fqb_last_scan_ms(fqb_ctx *ctx);
+/* the same for the kernel that turns the scan kernel's staged line ends / window descriptors into the dense
+ * line-end index (0 if the last call wrote no index through it) */
+float fqb_last_index_ms(fqb_ctx *ctx);
 
 /* ---- record filter: the step after the path (validate_dna / validate_dnan + Record::write) --------
  * Keeps the records whose seq() passes the predicate and writes their raw bytes ('@' .. final '\n',

@@ -16,11 +16,16 @@ import os
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "fastq_rs_b200", "csrc")
 spec = {
     "fq_stream.cu": regions(os.path.join(root, "fq_stream.cu"), [
-        (r"uint32_t nlbits3\(", "nlbits"), (r"Window win_load\(", "win_load"), (r"uint32_t win_scan_t\(", "win_scan"),
-        (r"uint32_t infer_start\(", "infer"), (r"^struct WinAcc", "srounds"), (r"bool stream_pass\(", "stream_pass"),
-        (r"^struct StreamCta", "prologue"), (r"// ---- where the first record", "first_window"),
-        (r"// ---- stream through the range", "loop_head"), (r"bool bad = false;", "loop_passes"),
-        (r"// line ends of the consumed records", "loop_tail"), (r"// ---- drain", "drain")]),
+        (r"uint32_t nlbits3\(", "nlbits"), (r"Window win_load\(", "win_load"), (r"void scan_rank_store\(", "win_scan"),
+        (r"uint32_t infer_start\(", "infer"), (r"^struct WinAcc", "srounds (8-lane scanned rounds)"),
+        (r"^struct FRounds", "frounds (predicted rounds)"), (r"bool no_newline32\(", "pred checks"),
+        (r"uint32_t stream_pass\(", "stream_pass"), (r"^struct StepK", "line_steps (var)"),
+        (r"^struct RecSink", "validate_block (var)"), (r"^struct Shape", "pred_pass / flex_pass"),
+        (r"uint32_t win_count_newlines\(", "win_count_newlines"), (r"bool desc_put\(", "desc / drain"),
+        (r"^struct RangeState", "var_loop"), (r"void __launch_bounds__\(C::NTHREADS, 1\) fq_stream_kernel", "prologue"),
+        (r"// ---- where the first record", "first_window"), (r"// ---- stream through the range", "loop_head"),
+        (r"// ---- scanned window ----", "loop_scanned"), (r"// line ends of the consumed records that lie in the owned bytes of the shard\n                n_lines", "loop_tail"),
+        (r"// ---- drain", "drain")]),
     "fq_hist.cuh": regions(os.path.join(root, "fq_hist.cuh"), [
         (r"void named_bar\(", "hist:asm_helpers"), (r"void trace_ev\(", "hist:trace"), (r"uint32_t nlmask16s7\(", "hist:nlmask"),
         (r"void flush_hist\(", "hist:flush"), (r"void account_record\(", "hist:account"), (r"record_global\(", "hist:record_global"),
