@@ -751,13 +751,18 @@ __device__ __forceinline__ uint32_t win_count_newlines(uint32_t buf_s, uint32_t 
     return __reduce_add_sync(0xffffffffu, cnt);
 }
 
-// one window descriptor of range rid (see ScanParams::desc); false if the range's share is full
-__device__ __forceinline__ bool desc_put(const ScanParams& p, uint32_t rid, uint32_t& dcount, int lane, uint32_t w0,
-                                         uint32_t w1, uint32_t w2, uint32_t w3)
+// one window descriptor of the warp's range (see ScanParams::desc): lanes 0..3 hold one word each (w01: lane 0 / 1,
+// w23: lanes 2 / 3 -- for predicted windows a per-shape constant); false if the range's share is full
+struct DescOut {
+    uint32_t* ptr;      // this lane's word of the next descriptor
+    uint32_t left;      // descriptors the range may still write
+};
+__device__ __forceinline__ bool desc_put(DescOut& d, int lane, uint32_t w0, uint32_t w1, uint32_t w23)
 {
-    if (dcount >= p.desc_cap) return false;
-    if (lane < 4) p.desc[((size_t)rid * p.desc_cap + dcount) * 4 + lane] = lane == 0 ? w0 : lane == 1 ? w1 : lane == 2 ? w2 : w3;
-    ++dcount;
+    if (d.left == 0) return false;
+    if (lane < 4) *d.ptr = lane == 0 ? w0 : lane == 1 ? w1 : w23;
+    d.ptr += 4;
+    --d.left;
     return true;
 }
 
@@ -1006,7 +1011,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
     unsigned long long cur = 0, lrank = 0;
     bool failed = false;
     uint32_t my_epoch = 0;
-    uint32_t dcount = 0;            // window descriptors written (the predicting variant; see ScanParams::desc)
+    // window descriptors of this range (the predicting variant; see ScanParams::desc)
+    const uint32_t rid0 = blockIdx.x * (uint32_t)C::NWARPS + (uint32_t)warp;
+    DescOut dout = {p.desc ? p.desc + ((size_t)rid0 * p.desc_cap) * 4 + (lane & 3) : nullptr, p.desc ? (uint32_t)p.desc_cap : 0u};
 
     if (live) {
         // ---- where the first record of the range starts -------------------------------------------
@@ -1046,7 +1053,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     }
                     failed = __any_sync(0xffffffffu, failed);
                     if (K && (unsigned long long)(w.src + (long long)list[c] - 1) >= p.n_own) failed = true;   // (a shard inside one record)
-                    if (!VAR && want_index && K && !desc_put(p, rid, dcount, lane, K, 0u, 0u, 0u)) failed = true;
+                    if (!VAR && want_index && K && !desc_put(dout, lane, K, 0u, 0u)) failed = true;
                     lrank = K;
                     if (lane == 0) p.res->line_phase = (int)((4u - K) & 3u);
                 }
@@ -1061,7 +1068,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         Shape sh = {0, 0, 0, 0, 0, 1};
         // per-lane constants of the shape (set with it): the byte this lane verifies in every record,
         // the line end this lane writes to the index, and how many records fit a window
-        uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0, gmask = 0;
+        uint32_t chk_off = 0, chk_exp = 0, chk_neg = 0, idx_le = 0, nfit_max = 0, nfit_rem = 0, gmask = 0, desc_w23 = 0;
         bool predict = false, flex = false;   // flex: header lengths vary, see flex_pass
         // a bad record in the LAST range of a shard that ends the stream needs no exact pass: every record in
         // front of it has been counted, nothing behind it has (tail_x = its offset)
@@ -1127,9 +1134,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
                     // the line ends of a predicted window are an arithmetic sequence: 16 bytes describe them
-                    const uint32_t o2 = sh.Lh + sh.Lsq;
-                    if (!desc_put(p, rid, dcount, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad,
-                                  (sh.Lh - 1u) | ((o2 - 1u) << 16), (o2 + sh.Lp - 1u) | (sh.reclen << 16))) {
+                    if (!desc_put(dout, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad, desc_w23)) {
                         failed = true;   // descriptor share too small: the exact path writes the index
                         break;
                     }
@@ -1165,9 +1170,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 next = w.pad + n_rec * sh.reclen;
                 if (want_index) {
                     // the line ends of a predicted window are an arithmetic sequence: 16 bytes describe them
-                    const uint32_t o2 = sh.Lh + sh.Lsq;
-                    if (!desc_put(p, rid, dcount, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad,
-                                  (sh.Lh - 1u) | ((o2 - 1u) << 16), (o2 + sh.Lp - 1u) | (sh.reclen << 16))) {
+                    if (!desc_put(dout, lane, n_lines | (1u << 24), (uint32_t)(p.stream_offset + w.src) + w.pad, desc_w23)) {
                         failed = true;   // descriptor share too small: the exact path writes the index
                         break;
                     }
@@ -1225,7 +1228,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 31u);
                 next = n_rec == n_fit2 ? s : nxt;
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share || !desc_put(p, rid, dcount, lane, n_lines, (uint32_t)lrank, 0u, 0u)) {
+                    if (lrank + n_lines > p.stage_share || !desc_put(dout, lane, n_lines, (uint32_t)lrank, 0u)) {
                         failed = true;
                         break;
                     }
@@ -1345,6 +1348,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                         idx_le = k == 0 ? sh.Lh - 1u : k == 1 ? o2 - 1u : k == 2 ? o2 + sh.Lp - 1u : sh.reclen - 1u;
                         nfit_max = (uint32_t)C::WIN / sh.reclen;
                         nfit_rem = (uint32_t)C::WIN - nfit_max * sh.reclen;
+                        // this lane's constant word of the window descriptors of this shape (lanes 2 and 3 write them)
+                        desc_w23 = (lane & 1) ? (o2 + sh.Lp - 1u) | (sh.reclen << 16) : (sh.Lh - 1u) | ((o2 - 1u) << 16);
                     }
                 }
                 // line ends of the consumed records that lie in the owned bytes of the shard
@@ -1355,7 +1360,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     n_lines = n_lines - 4u + (uint32_t)__popc(__ballot_sync(0xffffffffu, in));
                 }
                 if (want_index) {
-                    if (lrank + n_lines > p.stage_share || !desc_put(p, rid, dcount, lane, n_lines, (uint32_t)lrank, 0u, 0u)) {
+                    if (lrank + n_lines > p.stage_share || !desc_put(dout, lane, n_lines, (uint32_t)lrank, 0u)) {
                         failed = true;   // staging share too small: the exact path writes the index
                         break;
                     }
@@ -1404,7 +1409,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             sr.n_lines = lrank;
             sr.flags = failed ? 2u : (stopped ? 3u : 1u);
             // (no window predicted: every line end of the range is staged, back to back -- one plain copy)
-            sr.n_desc = (VAR || dbg_pred == 0) ? DESC_RAW_ONLY : dcount;
+            sr.n_desc = (VAR || dbg_pred == 0) ? DESC_RAW_ONLY : (uint32_t)p.desc_cap - dout.left;
             atomicAdd(&p.res->n_win_pred, (unsigned long long)dbg_pred);
             atomicAdd(&p.res->n_win_scan, (unsigned long long)dbg_scan);
             if (failed) atomicExch(&p.res->spec_fail, 1);
