@@ -832,6 +832,7 @@ struct RangeState {          // what the two loops over a range hand to each oth
     uint32_t epoch;              // last drain epoch this warp has served
     uint32_t dbg_scan;
     bool failed;
+    bool open_tail;              // the bytes of the shard end inside the record at `cur`, and more of the stream follows
 };
 
 template <class C>
@@ -840,6 +841,7 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
                                          StreamCta& cta, uint32_t rid, unsigned long long R1, bool last_eof,
                                          bool want_index, RangeState& rs, int warp, int lane, uint32_t lt_mask)
 {
+    const bool last_open = rid + 1u == p.n_sranges && !(p.flags & F_EOF) && p.n_avail == p.n_own;
     const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
     const RecSink sink = {p.stats, p.seqraw, lenh, p.max_len};
     const bool qhalf = lane >= 16;
@@ -869,6 +871,10 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
         const uint32_t n_win = min(total / 4u, (uint32_t)C::MAXR);   // complete records in the window
         if (n_win == 0 && last_eof && w.vlen < (uint32_t)C::WIN) {
             rs.tail_x = rs.cur;   // the stream ends inside this record (or in garbage): the first bad record
+            break;
+        }
+        if (n_win == 0 && last_open && w.vlen < (uint32_t)C::WIN) {
+            rs.open_tail = true;  // the bytes END inside this record and more will follow (a refill): carried over
             break;
         }
         if (n_win == 0) {
@@ -1075,13 +1081,17 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         // (not with an inferred shard start: that protocol has no classification step behind this kernel)
         const bool last_eof = rid + 1u == p.n_sranges && (p.flags & F_EOF) && !(p.flags & F_INFER_START) && p.n_avail == p.n_own;
         unsigned long long tail_x = NONE64;
+        // the shard's bytes end inside its last record and the stream goes on (FQB_F_PARTIAL refills, a shard without
+        // halo): no error and no reason for the exact path -- the record is reported as the tail to carry over
+        const bool last_open = rid + 1u == p.n_sranges && !(p.flags & F_EOF) && p.n_avail == p.n_own;
+        bool open_tail = false;
         uint32_t strikes = 0, cooldown = 0;
         uint32_t dbg_pred = 0, dbg_scan = 0;
         uint32_t acc_rec = 0;   // records of predicted windows not yet in the CTA's totals
         const uint32_t kA = fq_kmask[0], kB = fq_kmask[1];
         if (VAR) {
             // ---- reads of varying length: every window is scanned (var_loop) ---------------------------
-            RangeState rs = {cur, lrank, tail_x, parity, my_epoch, dbg_scan, failed};
+            RangeState rs = {cur, lrank, tail_x, parity, my_epoch, dbg_scan, failed, false};
             var_loop<C>(p, buf, buf_s, list, bar, hist, lenh, hist_s, cta, rid, R1, last_eof, want_index, rs, warp, lane,
                         lt_mask);
             cur = rs.cur;
@@ -1089,6 +1099,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
             tail_x = rs.tail_x;
             dbg_scan = rs.dbg_scan;
             failed = rs.failed;
+            open_tail = rs.open_tail;
         }
         while (!VAR && !failed && cur < R1 && cur < p.n_avail) {
             const Window w = win_load<C>(p, buf, bar, parity, (long long)cur, lane);
@@ -1262,6 +1273,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     tail_x = cur;    // the stream ends inside this record (or in garbage): the first bad record
                     break;
                 }
+                if (n_win == 0 && last_open && w.vlen < (uint32_t)C::WIN) {
+                    open_tail = true;   // the bytes END inside this record and more will follow (a refill): carried over
+                    break;
+                }
                 if (n_win == 0 || (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0))) {
                     failed = true;   // a record longer than the window, data ending inside a record, bytes >= 0x80
                     break;
@@ -1401,8 +1416,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 stopped = true;
             }
         }
+        if (open_tail && !failed && lane == 0) atomicMin(&p.res->tail_start, cur);
         // data that ends inside the owned bytes without a record boundary: not a clean shard
-        if (!failed && !stopped && cur < R1) failed = true;
+        if (!failed && !stopped && !open_tail && cur < R1) failed = true;
         if (lane == 0) {
             StreamRange& sr = p.sranges[rid];
             sr.end = cur;
@@ -1467,8 +1483,8 @@ __global__ void __launch_bounds__(1024) fq_stream_verify_kernel(const ScanParams
         if (sr.flags == 1u) {
             if (r + 1 < nlive) {
                 if (p.sranges[r + 1].first != sr.end) my_fail = min(my_fail, r + 1u);
-            } else if (sr.end < p.n_own || ((p.flags & F_EOF) && sr.end != p.n_avail)) {
-                my_fail = min(my_fail, r);
+            } else if ((sr.end < p.n_own && sr.end != p.res->tail_start) || ((p.flags & F_EOF) && sr.end != p.n_avail)) {
+                my_fail = min(my_fail, r);     // (tail_start: the incomplete last record of a shard that is carried over)
             }
         }
     }

@@ -758,6 +758,33 @@ def test_mid_stream_error_costs_at_most_two_parses(torch, oracle, eng):
         check_device_vs_oracle(torch, oracle, eng, bytes(data))
 
 
+def test_refill_that_ends_inside_a_record_stays_on_the_fast_path(torch, oracle, eng, eng300):
+    """FQB_F_PARTIAL refills (and shards without a halo) normally end inside a record: that record is the tail to carry
+    over (fqb_result.tail_offset), not a reason to redo the chunk on the exact path."""
+    fixed = oracle.synth_fixed_records(30000).tobytes()
+    var = oracle.synth_var(20000).tobytes()
+    for engine, data in ((eng, fixed), (eng300, var), (eng, var)):
+        ores, oidx = oracle.each_index(data)
+        for cut in (len(data) - 1, len(data) - 100, len(data) * 2 // 3, 70001):
+            part = data[:cut]
+            n_ok = int(np.searchsorted(oidx[:, 4], cut, side="left"))       # records complete inside the part
+            tail = int(oidx[n_ok, 0]) if n_ok < len(oidx) and int(oidx[n_ok, 0]) < cut else None
+            for hist in (True, False):
+                out, st, idx = engine.parse_host(part, hist=hist, want_index=True, want_stats=hist, partial=True, stream_offset=32)
+                assert (out.status, out.n_records) == (0, n_ok), (cut, out)
+                assert out.tail_offset == (None if tail is None else tail + 32)
+                assert not engine.last_path()["exact"], (cut, hist, engine.max_len)
+                np.testing.assert_array_equal(idx[:4 * n_ok].reshape(n_ok, 4), oidx[:n_ok, 1:5] + 32)
+                if hist:
+                    _, ost = oracle.each_stats(data[:int(oidx[n_ok - 1, 4]) + 1], engine.max_len)
+                    assert_stats_equal(st, ost)
+            # the same through fqb_parse_device: a shard that is all there is for now (no halo, not the end of the stream)
+            t = to_dev(torch, part)
+            engine.parse_device(t, n_own=cut, n_avail=cut, hist=True, eof=False)
+            out, _ = engine.fetch()
+            assert (out.status, out.n_records, out.tail_offset) == (0, n_ok, tail) and not engine.last_path()["exact"]
+
+
 def test_count_mode_varying_shapes(torch, oracle, eng):
     data = b"".join(_plain_rec(b"r%d" % i, 60 + 13 * ((i // 5) % 7), i) for i in range(9000))
     check_count_mode(torch, oracle, eng, data)
