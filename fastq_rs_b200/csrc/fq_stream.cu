@@ -327,23 +327,35 @@ struct SRounds<C, C::NCHUNK> {
     }
 };
 
-// The same rounds for records of a predicted shape with seq() and qual() of one length n: only the last round
-// is partial, and which of a lane's four bumps of that round lie inside the line is the same for every record
-// of the shape -- byte k of gm is 1 where the k-th bump counts (0 for lanes without a record), so the guard is
+// The same rounds for records of a predicted shape with seq() and qual() of one length n, NR = ceil(n / 32) rounds
+// known at compile time (the caller dispatches once per window): straight-line code, no branch between the rounds,
+// and the words of round T + 1 are loaded before the bumps of round T (shared-memory atomics and loads stay in
+// program order, so the loads would otherwise wait behind them and the funnel shift behind the loads).  Only the last
+// round can be partial, and which of a lane's four bumps of that round lie inside the line is the same for every
+// record of the shape -- byte k of gm is 1 where the k-th bump counts (0 for lanes without a record), so the guard is
 // one PRMT per bump instead of a compare and a select.
-template <class C, int T>
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32_ordered(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <class C, int NR, int T>
 struct FRounds {
-    static __device__ __forceinline__ void run(uint32_t as0, uint32_t aq0, uint32_t shs, uint32_t shq, uint32_t n,
-                                               uint32_t inc_s, uint32_t inc_q, uint32_t gm, const LaneK& lc, uint32_t& hib)
+    static __device__ __forceinline__ void run(uint32_t as0, uint32_t aq0, uint32_t shs, uint32_t shq, uint32_t s0,
+                                               uint32_t s1, uint32_t q0, uint32_t q1, uint32_t inc_s, uint32_t inc_q,
+                                               uint32_t gm, const LaneK& lc, uint32_t& hib)
     {
-        if (32u * T >= n) return;                                         // warp-uniform
-        const uint32_t s0 = lds32<32 * T>(as0), s1 = lds32<32 * T + 4>(as0);
-        const uint32_t q0 = lds32<32 * T>(aq0), q1 = lds32<32 * T + 4>(aq0);
         const uint32_t vs = __funnelshift_r(s0, s1, shs);
         const uint32_t vq = __funnelshift_r(q0, q1, shq);
+        if (T + 1 < NR) {
+            s0 = lds32_ordered<32 * (T + 1)>(as0), s1 = lds32_ordered<32 * (T + 1) + 4>(as0);
+            q0 = lds32_ordered<32 * (T + 1)>(aq0), q1 = lds32_ordered<32 * (T + 1) + 4>(aq0);
+        }
         hib |= vs | vq;
         constexpr int CO = 4 * C::CHUNK_WORDS * T;
-        if (32u * (T + 1) <= n) {
+        if (T + 1 < NR) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 red_add<CO>(dp4a_u(vs, lc.wsel[k], lc.hk[k]), inc_s);
@@ -356,16 +368,26 @@ struct FRounds {
                 red_add<CO>(dp4a_u(vq, lc.wsel[k], lc.hk[k]), __byte_perm(gm, 0u, 0x4044u + ((uint32_t)k << 8)));
             }
         }
-        FRounds<C, T + 1>::run(as0, aq0, shs, shq, n, inc_s, inc_q, gm, lc, hib);
+        FRounds<C, NR, T + 1>::run(as0, aq0, shs, shq, s0, s1, q0, q1, inc_s, inc_q, gm, lc, hib);
     }
 };
-template <class C>
-struct FRounds<C, C::NCHUNK> {
+template <class C, int NR>
+struct FRounds<C, NR, NR> {
     static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                                               uint32_t, const LaneK&, uint32_t&)
+                                               uint32_t, uint32_t, uint32_t, uint32_t, const LaneK&, uint32_t&)
     {
     }
 };
+template <class C, int NR>
+__device__ __forceinline__ void frounds(uint32_t sa, uint32_t qa, uint32_t inc_s, uint32_t inc_q, uint32_t gm,
+                                        const LaneK& lc, uint32_t& hib)
+{
+    if (NR == 0) return;
+    const uint32_t as0 = sa & ~3u, aq0 = qa & ~3u;
+    const uint32_t s0 = lds32_ordered<0>(as0), s1 = lds32_ordered<4>(as0);
+    const uint32_t q0 = lds32_ordered<0>(aq0), q1 = lds32_ordered<4>(aq0);
+    FRounds<C, NR, 0>::run(as0, aq0, sa << 3, qa << 3, s0, s1, q0, q1, inc_s, inc_q, gm, lc, hib);
+}
 
 // bytes [from, to) of the window (to - from <= 32) hold no '\n': lane i of the 8-lane group looks at
 // the 4 bytes from + 4i .. (two aligned words, funnel shift); lane-local answer, the caller votes
@@ -664,9 +686,9 @@ struct Shape {
     uint32_t reclen;
 };
 
-template <class C>
+template <class C, int NR>
 __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, uint32_t pad, uint32_t chk_off,
-                                              uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t gm,
+                                              uint32_t chk_exp, uint32_t chk_neg, uint32_t gm,
                                               const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
                                               uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
 {
@@ -691,9 +713,9 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     // hib: OR of every word the rounds look at.  A byte >= 0x80 makes the dp4a address leave its row --
     // still inside this CTA's shared memory (at most 32 KB above the table: the length histogram and
     // window buffers), so nothing faults; the caller raises spec_fail and the exact path redoes the shard.
-    // (ns, nq are the same for every record of the window: the guards of the last, partial round do
+    // (the line length is the same for every record of the window: the guards of the last, partial round do
     // not depend on the pass, only the increments do)
-    FRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
+    frounds<C, NR>(sa, qa, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
     return first_bad;
 }
 
@@ -701,9 +723,9 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
 // window offset of record r and its header length (found by the caller's search for the first '\n' behind the
 // record start, so the header line needs no further check); everything behind the header is predicted from
 // the shape and verified as in pred_pass.  chk_rel: the byte lane i verifies, relative to the sequence line.
-template <class C>
+template <class C, int NR>
 __device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, uint32_t my_start, uint32_t my_lh,
-                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t ns, uint32_t gm,
+                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t gm,
                                               const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
                                               uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
 {
@@ -724,9 +746,40 @@ __device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, u
     }
     const uint32_t sa = body + 4u * i;
     const uint32_t qa = sa + sh.Lsq + sh.Lp;
-    FRounds<C, 0>::run(sa & ~3u, qa & ~3u, sa << 3, qa << 3, ns, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
+    frounds<C, NR>(sa, qa, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
     return first_bad;
 }
+
+// All passes of a predicted window, dispatched once on the number of rounds NR = ceil(n / 32) of its shape
+template <class C, bool FLEX, int NR>
+struct PredWindow {
+    static __device__ __forceinline__ uint32_t run(uint32_t nr, uint32_t buf_s, const Shape& sh, uint32_t pad,
+                                                   uint32_t my_start, uint32_t my_lh, uint32_t chk_off, uint32_t chk_exp,
+                                                   uint32_t chk_neg, uint32_t gm, const LaneK& lc, uint32_t hist_s,
+                                                   uint32_t n_rec, uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB,
+                                                   uint32_t& hib)
+    {
+        if (nr != (uint32_t)NR)
+            return PredWindow<C, FLEX, NR - 1>::run(nr, buf_s, sh, pad, my_start, my_lh, chk_off, chk_exp, chk_neg, gm, lc,
+                                                    hist_s, n_rec, sub, i, kA, kB, hib);
+        uint32_t first_bad = NO_START;
+        for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
+            first_bad = FLEX ? flex_pass<C, NR>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, gm, lc, hist_s, n_rec,
+                                                pass, sub, i, kA, kB, hib)
+                             : pred_pass<C, NR>(buf_s, sh, pad, chk_off, chk_exp, chk_neg, gm, lc, hist_s, n_rec, pass, sub,
+                                                i, kA, kB, hib);
+        return first_bad;
+    }
+};
+template <class C, bool FLEX>
+struct PredWindow<C, FLEX, -1> {
+    static __device__ __forceinline__ uint32_t run(uint32_t, uint32_t, const Shape&, uint32_t, uint32_t, uint32_t, uint32_t,
+                                                   uint32_t, uint32_t, uint32_t, const LaneK&, uint32_t, uint32_t, uint32_t,
+                                                   uint32_t, uint32_t, uint32_t, uint32_t&)
+    {
+        return 0u;   // (not reached: nr <= NCHUNK by the predict condition)
+    }
+};
 
 // '\n' count of a full window at positions >= pad (no list, no ranks: ~1/3 of the scan)
 template <class C>
@@ -1156,10 +1209,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 if (room < (unsigned long long)C::WIN) n_rec = min(n_fit, ((uint32_t)room - w.pad + sh.reclen - 1u) / sh.reclen);
                 const uint32_t Lr = sh.Lsq - 1u;
                 const uint32_t Ls = Lr - sh.cr_s;                           // seq()/qual() drop one trailing '\r' (cr_s == cr_q)
-                uint32_t first_bad = NO_START, hib = 0;
-                for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = pred_pass<C>(buf_s, sh, w.pad, chk_off, chk_exp, chk_neg, Ls, gmask, lc, hist_s, n_rec, pass,
-                                             sub, li, kA, kB, hib);
+                uint32_t hib = 0;
+                const uint32_t first_bad = PredWindow<C, false, C::NCHUNK>::run((Ls + 31u) >> 5, buf_s, sh, w.pad, 0u, 0u, chk_off,
+                                                                                chk_exp, chk_neg, gmask, lc, hist_s, n_rec, sub,
+                                                                                li, kA, kB, hib);
                 if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;   // bytes >= 0x80 reached the rounds: the exact path
                     break;
@@ -1217,10 +1270,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                 n_rec = n_fit2;
                 const uint32_t Lr = sh.Lsq - 1u;
                 const uint32_t Ls = Lr - sh.cr_s;
-                uint32_t first_bad = NO_START, hib = 0;
-                for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-                    first_bad = flex_pass<C>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, Ls, gmask, lc, hist_s, n_rec,
-                                             pass, sub, li, kA, kB, hib);
+                uint32_t hib = 0;
+                const uint32_t first_bad = PredWindow<C, true, C::NCHUNK>::run((Ls + 31u) >> 5, buf_s, sh, 0u, my_start, my_lh,
+                                                                               chk_off, chk_exp, chk_neg, gmask, lc, hist_s, n_rec,
+                                                                               sub, li, kA, kB, hib);
                 if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;
                     break;
@@ -1337,7 +1390,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                               (HIST ? (sh.Lsq - 1u <= Pm && sh.Lp <= 34u && sh.cr_s == sh.cr_q) : all_h);
                     if (HIST && predict) {
                         // which bumps of the last, partial round lie inside seq() / qual() (see FRounds)
-                        const uint32_t n = sh.Lsq - 1u - sh.cr_s, base = (n & ~31u) + 4u * li;
+                        const uint32_t n = sh.Lsq - 1u - sh.cr_s, base = ((n - 1u) & ~31u) + 4u * li;   // (n == 0: no round)
                         gmask = 0;
 #pragma unroll
                         for (uint32_t k = 0; k < 4; ++k)
