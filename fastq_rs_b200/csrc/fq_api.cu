@@ -79,11 +79,13 @@ __global__ void __launch_bounds__(PROBE_THREADS) fq_init_kernel(DevResult* r, in
             if (pos[j + 1] - pos[j] != pos[j + 5] - pos[j + 4]) varies |= 1u << (j & 3);
         if (varies) atomicOr(&s_varies, varies);
         __syncthreads();
-        shape_var = (nl >= 16 && __popc(s_varies) >= 2) ? 1 : 0;
-        // bytes >= 0x80 (UTF-8 in the id lines, say): the predicting variant leaves the fast path at the first
-        // window it has to scan that holds one; the variable-length variant only minds them in the sequence and
-        // quality lines themselves
-        if (s_hi) shape_var = 1;
+        // (probe == 2, no histograms: the predicting variant needs every line length fixed there -- it checks a
+        // window by its '\n' count --, so any kind that varies sends the launch to the variable-length variant)
+        shape_var = (nl >= 16 && __popc(s_varies) >= (probe == 2 ? 1 : 2)) ? 1 : 0;
+        // bytes >= 0x80 (UTF-8 in the id lines, say): with histograms the predicting variant leaves the fast path at
+        // the first window it has to scan that holds one; the variable-length variant only minds them in the
+        // sequence and quality lines themselves
+        if (s_hi && probe == 1) shape_var = 1;
     }
     if (t != 0) return;
     r->shape_var = shape_var;
@@ -530,7 +532,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
     if (ctx->d_trace) CK(cudaMemsetAsync(ctx->d_trace, 0, (size_t)ctx->num_sms * TRACE_K * 16 * 8, st));
 
     fq_init_kernel<<<1, PROBE_THREADS, 0, st>>>(ctx->d_res, fast ? 0 : 1, (int)(sh->line_base & 3), sh->d_bytes, sh->n_avail,
-                                     (fast && (sh->flags & FQB_F_HIST) && !getenv("FQB_NO_VAR")) ? 1 : 0);
+                                     (fast && !getenv("FQB_NO_VAR")) ? ((sh->flags & FQB_F_HIST) ? 1 : 2) : 0);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_stats, 0, (ctx->nwords + 8 * (size_t)FQB_MAX_WORLD) * 8, st));   // block + outcome slots
     CK(cudaMemsetAsync(ctx->d_seqraw, 0, (size_t)ctx->P * 256 * 8, st));
@@ -543,7 +545,7 @@ static int enqueue_parse(fqb_ctx* ctx, const fqb_shard* sh, cudaStream_t st, Dev
             CK(launch_stream(p, ctx->nchunk, ctx->grid, st));
             if (timed) CK(cudaEventRecord(ctx->ev1, st));
             CK(launch_stream_verify(p, carry, st));
-            ctx->launches += (p.flags & F_HIST) ? 3 : 2;
+            ctx->launches += 3;   // (both variants of the speculative kernel + the chain check)
         }
         // exact path (every launch of it returns at once unless res->spec_fail is set): newline counts
         // of the CTA ranges -> exact line numbers -> exact kernel.  It needs the exact line_base: with

@@ -888,7 +888,7 @@ struct RangeState {          // what the two loops over a range hand to each oth
     bool open_tail;              // the bytes of the shard end inside the record at `cur`, and more of the stream follows
 };
 
-template <class C>
+template <class C, bool HIST>
 __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint32_t buf_s, uint16_t* list,
                                          unsigned long long* bar, uint32_t* hist, uint32_t* lenh, uint32_t hist_s,
                                          StreamCta& cta, uint32_t rid, unsigned long long R1, bool last_eof,
@@ -898,8 +898,8 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
     const uint32_t Pm = p.max_len < (uint32_t)C::PPAD ? p.max_len : (uint32_t)C::PPAD;
     const RecSink sink = {p.stats, p.seqraw, lenh, p.max_len};
     const bool qhalf = lane >= 16;
-    StepK sk;
-    {
+    StepK sk = {};
+    if (HIST) {
         const uint32_t sub = (uint32_t)lane >> 3, i = (uint32_t)lane & 7u;
         sk.lane_pos = 4u * ((uint32_t)lane & 15u);
         sk.lane_base = buf_s + sk.lane_pos;
@@ -946,15 +946,17 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
         uint32_t first_bad = NO_START, hib = 0, lob = 0xFFFFFFFFu;
         for (uint32_t b0 = 0; b0 < n_rec && first_bad == NO_START; b0 += 32u) {
             uint32_t ps, pq;
-            first_bad = validate_block<C, true>(sink, buf, buf_s, Pm, n_rec, b0, lane, ps, pq, wa);
-            const uint32_t cnt = min(min(n_rec, first_bad) - b0, 32u);
-            for (uint32_t r = 0; r < cnt; ++r)
-                line_steps<C>(__shfl_sync(0xffffffffu, ps, r), __shfl_sync(0xffffffffu, pq, r), qhalf, sk, hib, lob);
+            first_bad = validate_block<C, HIST>(sink, buf, buf_s, Pm, n_rec, b0, lane, ps, pq, wa);
+            if (HIST) {
+                const uint32_t cnt = min(min(n_rec, first_bad) - b0, 32u);
+                for (uint32_t r = 0; r < cnt; ++r)
+                    line_steps<C>(__shfl_sync(0xffffffffu, ps, r), __shfl_sync(0xffffffffu, pq, r), qhalf, sk, hib, lob);
+            }
         }
         // bytes >= 0x80 (or below the first row of the table) in a sequence or quality line -- id and separator
         // lines may hold anything --: their bumps left the table rows, the exact path redoes the shard
-        if (C::ROW0) hib |= ~lob << 1;                         // bit 7 of a byte lane: some byte there was < 32
-        if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
+        if (HIST && C::ROW0) hib |= ~lob << 1;                 // bit 7 of a byte lane: some byte there was < 32
+        if (HIST && __any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
             rs.failed = true;
             break;
         }
@@ -997,7 +999,7 @@ __device__ __forceinline__ void var_loop(const ScanParams& p, uint8_t* buf, uint
         rs.lrank += n_lines;
         rs.cur = w.src + next;
         if (rs.tail_x != NONE64) break;
-        drain_tick<C>(hist, p, cta, n_rec, rs.epoch, warp, lane);   // u16 counter halves
+        if (HIST) drain_tick<C>(hist, p, cta, n_rec, rs.epoch, warp, lane);   // u16 counter halves
     }
 }
 
@@ -1145,8 +1147,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
         if (VAR) {
             // ---- reads of varying length: every window is scanned (var_loop) ---------------------------
             RangeState rs = {cur, lrank, tail_x, parity, my_epoch, dbg_scan, failed, false};
-            var_loop<C>(p, buf, buf_s, list, bar, hist, lenh, hist_s, cta, rid, R1, last_eof, want_index, rs, warp, lane,
-                        lt_mask);
+            var_loop<C, HIST>(p, buf, buf_s, list, bar, hist, lenh, hist_s, cta, rid, R1, last_eof, want_index, rs, warp, lane,
+                              lt_mask);
             cur = rs.cur;
             lrank = rs.lrank;
             tail_x = rs.tail_x;
@@ -1698,7 +1700,8 @@ using VCfg5 = SCfg<5, 28, 4096, 1>;
 using VCfg10 = SCfg<10, 22, 4096, 1, 32>;   // rows 32 .. 127 only: 124 KB of counters leave room for 4 KiB windows
 static_assert(VCfg5::NWARPS == SCfg5H::NWARPS && VCfg10::NWARPS == SCfg10::NWARPS, "both variants walk the same ranges");
 
-int stream_warps(int nchunk, bool hist) { return nchunk <= 5 ? (hist ? SCfg5H::NWARPS : SCfg5::NWARPS) : SCfg10::NWARPS; }
+// (without histograms there is no counter table: 32 warps x 4 KiB windows whatever the maximum read length)
+int stream_warps(int nchunk, bool hist) { return !hist ? SCfg5::NWARPS : nchunk <= 5 ? SCfg5H::NWARPS : SCfg10::NWARPS; }
 
 template <class C, class H, class V>
 static cudaError_t configure_set()
@@ -1706,6 +1709,8 @@ static cudaError_t configure_set()
     cudaError_t e = cudaFuncSetAttribute(fq_stream_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H::TOTAL);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(fq_stream_kernel<V, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V::TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fq_stream_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fq_stream_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
 }
@@ -1726,12 +1731,13 @@ static void launch_set(const ScanParams& p, int grid, cudaStream_t st)
         fq_stream_kernel<V, true, true><<<grid, V::NTHREADS, V::TOTAL, st>>>(p);
     } else {
         fq_stream_kernel<C, false, false><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
+        fq_stream_kernel<C, false, true><<<grid, C::NTHREADS, C::TOTAL, st>>>(p);
     }
 }
 
 cudaError_t launch_stream(const ScanParams& p, int nchunk, int grid, cudaStream_t st)
 {
-    if (nchunk <= 5)
+    if (nchunk <= 5 || !(p.flags & F_HIST))
         launch_set<SCfg5, SCfg5H, VCfg5>(p, grid, st);
     else
         launch_set<SCfg10, SCfg10, VCfg10>(p, grid, st);

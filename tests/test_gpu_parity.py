@@ -700,11 +700,21 @@ def test_variable_length_variant(what, torch, oracle, eng, eng300):
     elif what == "ctrl_in_header":
         recs = [r.replace(b"@r", b"@\t\x01", 1) for r in recs]
     data = b"".join(recs)
+    ores, oidx = oracle.each_index(data)
     for engine in (eng300, eng):
         check_device_vs_oracle(torch, oracle, engine, data)
         p = engine.last_path()
         if what in ("clean", "high_in_header", "ctrl_in_header", "lengths_64k", "crlf", "clip"):
             assert not p["exact"], (what, engine.max_len, p)          # served by the fast path
+        # the same variant without histograms (delimit + line-end index; any byte may stand anywhere in a line)
+        t = to_dev(torch, data)
+        idx = torch.zeros(len(data) + 8, dtype=torch.int32, device="cuda")
+        engine.parse_device(t, n_own=len(data), n_avail=len(data), hist=False, index=idx)
+        out, _ = engine.fetch(want_stats=False)
+        assert (out.status, out.n_records, out.n_lines) == (ores.status, ores.n_records, data.count(b"\n"))
+        got = idx[:4 * out.n_records].cpu().numpy().view(np.uint32).astype(np.uint64).reshape(-1, 4)
+        np.testing.assert_array_equal(got, oidx[:, 1:5])
+        assert not engine.last_path()["exact"], (what, engine.max_len)
 
 
 def test_mid_stream_error_costs_at_most_two_parses(torch, oracle, eng):
