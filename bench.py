@@ -196,7 +196,10 @@ def workload_config(args, n_gpus):
                         "+ per-position ACGTN and quality histograms (BASELINE configs[1]+[2], one fused pass)",
             "read_len": READ_LEN, "record_bytes": REC_BYTES, "bytes_per_gpu": int(args.gib * GIB),
             "sharding": f"byte-chunk x{n_gpus}" if n_gpus > 1 else "none",
-            "l2": "inputs (GiBs) far larger than the 126 MB L2; no flush needed"}
+            "l2": "inputs (GiBs) far larger than the 126 MB L2; no flush needed",
+            "pipeline": "1 context: every step is read back before the next is enqueued" if args.no_pipeline else
+                        "2 engine contexts take the steps in turn: step k+1 is enqueued behind step k's kernels before the "
+                        "host reads step k's result (the GPU still runs the steps one after the other)"}
 
 
 def sharded_bit_exact_check(fq, eng, sp, dist, world, rank, dev):
@@ -294,18 +297,53 @@ def run_ours(args):
     spec = ShardSpec(buf[16 - front:], a, b, halo, front, is_last=(b + halo == total))
     check = sharded_bit_exact_check(fq, eng, sp, dist, world, rank, dev) if world > 1 else None
 
-    def step():
-        """One pass of the hot path over this rank's shard (+ the one collective when sharded)."""
-        if world > 1:
-            return sp.parse(spec, hist=True, index=index)
-        eng.parse_device(data, n_own=n_own, n_avail=n_avail, hist=True, index=index, line_base=0,
-                         stream_offset=a, line_start=True, front16=False, eof=True)
-        return eng.fetch()
+    # Two engine contexts take the steps in turn: step k + 1 is enqueued (on its own stream, behind step k's kernels)
+    # before the host waits for step k's result, so the copy of the result and the host-side bookkeeping of one step
+    # overlap the kernels of the next.  On the GPU the steps still run one after the other.
+    depth = 1 if args.no_pipeline else 2
+    engs, sps, idxs = [eng], [sp], [index]
+    if depth == 2:
+        engs.append(fq.Engine(max_len=READ_LEN, device=local, slot_bytes=args.slot_mib << 20, n_slots=3))
+        sps.append(ShardedParser(engs[1], dist=dist if world > 1 else None, device=dev))
+        idxs.append(torch.empty_like(index))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    for s_ in streams:
+        s_.wait_stream(torch.cuda.current_stream())
+    scan_ms, index_ms = [], []
 
-    for _ in range(args.warmup):
-        out, st = step()
+    def begin(k):
+        """Enqueue one pass of the hot path over this rank's shard (+ the one collective when sharded)."""
+        j = k % depth
+        if depth == 2:
+            streams[j].wait_stream(streams[j ^ 1])
+        with torch.cuda.stream(streams[j]):
+            if world > 1:
+                sps[j].begin(spec, hist=True, index=idxs[j])
+            else:
+                engs[j].parse_device(data, n_own=n_own, n_avail=n_avail, hist=True, index=idxs[j], line_base=0,
+                                     stream_offset=a, line_start=True, front16=False, eof=True)
+
+    def end(k):
+        """Wait for step k: its global (Outcome, Stats) on the host."""
+        j = k % depth
+        with torch.cuda.stream(streams[j]):
+            r = sps[j].finish() if world > 1 else engs[j].fetch()
+        scan_ms.append(engs[j].last_scan_ms())
+        index_ms.append(engs[j].last_index_ms())
+        return r
+
+    def run_steps(n):
+        r = None
+        begin(0)
+        for k in range(1, n):
+            begin(k)
+            r = end(k - 1)
+            assert r[0].status == 0, r[0]
+        return end(n - 1)
+
+    out, st = run_steps(max(args.warmup, depth))
     assert out.status == 0, out
-    assert sp.reparsed == 0, "an inferred shard start was not confirmed"
+    assert all(x.reparsed == 0 for x in sps), "an inferred shard start was not confirmed"
     assert st.n_records == total // REC_BYTES, (st.n_records, total // REC_BYTES)
     assert int(st.qual_hist.sum()) == READ_LEN * st.n_records
 
@@ -315,21 +353,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- timed region: HBM-resident ---------------------------------------------------------
-    launches0 = eng.launch_count()
-    coll0 = sp.collectives
-    scan_ms, index_ms = [], []
+    launches0 = sum(e.launch_count() for e in engs)
+    coll0 = sum(x.collectives for x in sps)
+    scan_ms.clear()
+    index_ms.clear()
     with ClockSampler(local) as clk:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            step()
-            scan_ms.append(eng.last_scan_ms())
-            index_ms.append(eng.last_index_ms())
+        run_steps(args.steps)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
+    launches = sum(e.launch_count() for e in engs) - launches0
+    colls = sum(x.collectives for x in sps) - coll0
+    for e in engs[1:]:
+        e.close()
+    del idxs[1:], sps[1:], engs[1:]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -405,7 +445,7 @@ def run_ours(args):
         if configs is not None:
             line["configs"] = configs
         if world > 1:
-            line["collectives_per_step"] = (sp.collectives - coll0) / args.steps
+            line["collectives_per_step"] = colls / args.steps
             line["sharded_check"] = check
     if e2e is not None:
         ev = torch.tensor([e2e["bytes"], e2e["seconds"]], dtype=torch.float64, device=dev)
@@ -499,6 +539,7 @@ def main():
     ap.add_argument("--slot-mib", type=int, default=64)
     ap.add_argument("--cpu-sample-gib", type=float, default=2.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one engine context: read every step back before the next")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration list (N = 1 line)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -35,6 +35,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a global range (16-byte granular; no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // potentially blocking probe: the warp is suspended until the phase completes or the time hint
 // (ns) runs out, so waiting warps do not burn issue slots
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)

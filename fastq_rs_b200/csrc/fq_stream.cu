@@ -137,6 +137,13 @@ __device__ __forceinline__ Window win_load(const ScanParams& p, uint8_t* buf, un
         fence_proxy_async();
         mbar_arrive_expect_tx(bar, bulk);
         if (bulk) bulk_g2s(buf, p.data + w.src, bulk, bar);
+#ifndef FQ_NO_L2_PREFETCH
+        // the window after this one starts somewhere in the last few hundred bytes of it: have L2 fetch what follows
+        // while this window is being worked on (the warp has one buffer; this turns the next load's DRAM latency
+        // into an L2 hit)
+        if (w.vlen == (uint32_t)C::WIN && w.src + 2 * C::WIN <= (long long)p.n_avail)
+            bulk_prefetch_l2(p.data + w.src + C::WIN, (uint32_t)C::WIN);
+#endif
     }
     // the bytes the 16-byte-granular bulk copy leaves out (last window of the shard only)
     if ((w.vlen & 15u) && (uint32_t)lane < (w.vlen & 15u)) buf[bulk + lane] = p.data[w.src + bulk + lane];

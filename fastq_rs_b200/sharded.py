@@ -124,9 +124,29 @@ class ShardedParser:
         """Delimit (+histograms) the whole stream; every rank returns the GLOBAL (Outcome, Stats).
         `index` (optional int32 tensor) receives this rank's line ends (low 32 bits of the stream
         offsets of the '\n' in [a, b))."""
+        self.begin(sh, hist, index)
+        return self.finish()
+
+    def begin(self, sh: ShardSpec, hist: bool = True, index=None):
+        """The asynchronous half of parse(): the shard's parse and the one collective are enqueued on the current
+        stream, nothing is waited for.  A caller with two parsers (two engine contexts) can enqueue the next
+        stream's shard before it reads this one's result with finish()."""
         infer = sh.a != 0 and sh.b > sh.a
+        self._pending = (sh, hist, index, infer)
         self._enqueue(sh, hist, index, 0, infer)
-        words, g = self._reduce()
+        self.collectives += 1
+        if self.native:
+            self.eng.allreduce()
+
+    def finish(self):
+        """Wait for begin()'s collective; the GLOBAL (Outcome, Stats) on every rank."""
+        sh, hist, index, infer = self._pending
+        self._pending = None
+        if self.native:
+            words, g = self.eng.fetch_reduced()
+        else:
+            self.collectives -= 1
+            words, g = self._reduce()
         lb = np.concatenate([[0], np.cumsum(g[:-1, 3])])            # exact line numbers: prefix of the n_lines
         if bool((g[:, 0] == OK).all()) and self._phases_ok(g, lb):
             total = Outcome(status=OK, finished=bool(g[-1, 1]), n_records=int(g[:, 2].sum()),
