@@ -1661,6 +1661,16 @@ __global__ void __launch_bounds__(256) fq_stream_compact_kernel(const ScanParams
                     base += total;
                     continue;
                 }
+                if (all_cont && (f.x >> 24) == 1u && ((reinterpret_cast<uintptr_t>(dst + base) & 15) == 0) && base + total <= n) {
+                    // (the usual alignment: whole records in front) one 16-byte store per record
+                    const uint32_t l0 = f.z & 0xFFFFu, l1 = f.z >> 16, l2 = f.w & 0xFFFFu, l3 = reclen - 1u;
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + base);
+                    uint32_t v = f.y + (uint32_t)t * reclen;
+                    for (uint32_t r = t; r < total / 4u; r += 256u, v += 256u * reclen)
+                        d4[r] = make_uint4(v + l0, v + l1, v + l2, v + l3);
+                    base += total;
+                    continue;
+                }
                 if (all_cont && (f.x >> 24) == 1u) {
                     const uint32_t le = k4 == 0 ? (f.z & 0xFFFFu) : k4 == 1 ? (f.z >> 16) : k4 == 2 ? (f.w & 0xFFFFu) : reclen - 1u;
                     uint32_t v = f.y + ((uint32_t)t >> 2) * reclen + le;
@@ -1759,7 +1769,9 @@ cudaError_t launch_stream_verify(const ScanParams& p, DevCarry* carry, cudaStrea
 
 cudaError_t launch_stream_compact(const ScanParams& p, DevCarry* carry, int grid, cudaStream_t st)
 {
-    fq_stream_compact_kernel<<<grid * 8, 256, 0, st>>>(p, carry);
+    // one block per range (they are equally long): no block is left with a range more than the others
+    (void)grid;
+    fq_stream_compact_kernel<<<p.n_sranges ? p.n_sranges : 1u, 256, 0, st>>>(p, carry);
     return cudaGetLastError();
 }
 
