@@ -7,7 +7,10 @@ A step = one pass of the hot path over one batch of synthetic 150 bp FASTQ (SURV
 input A): newline / record-boundary scan with '@'/'+' validation, the line-end index, and the
 per-position ACGTN + quality-byte histograms, fused in one sm_100a kernel (fq_stream.cu).
 
-  value     whole-job GB/s with the bytes already resident in HBM (CUDA events, max over ranks)
+  value     whole-job GB/s with the bytes already resident in HBM (CUDA events, max over ranks).  Two engine
+            contexts take the steps in turn: step k+1 is enqueued behind step k's kernels before the host reads
+            step k's result, so the read-back overlaps the next step's kernels (--no-pipeline: one context)
+  configs   (N = 1) every BASELINE configuration through the same API, one context
   e2e       same metric through the host API (fqb_parse_host): pinned host bytes -> H2D -> kernels
             -> D2H of the outcome + stats block, every step
   roofline  the scan kernel against the measured HBM bandwidth (MEASURED_PEAKS.json)
