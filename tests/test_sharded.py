@@ -28,7 +28,19 @@ def _worker(rank, world, init_file, data_bytes, mode, q):
     t = torch.from_numpy(data[a - front:b + halo].copy())
     eng = FakeEngine(150, lie_phase=(mode == "lie" and rank == 1), fail_infer=(mode == "nophase"))
     sp = ShardedParser(eng, dist=dist)
-    out, st = sp.parse(ShardSpec(t, a, b, halo, front, is_last=(b + halo == total)))
+    spec = ShardSpec(t, a, b, halo, front, is_last=(b + halo == total))
+    if mode == "two_in_flight":
+        # begin / finish: a second parser (its own engine context) takes the next step before the first is read
+        eng2 = FakeEngine(150)
+        sp2 = ShardedParser(eng2, dist=dist)
+        sp.begin(spec)
+        sp2.begin(spec)
+        out, st = sp.finish()
+        out2, st2 = sp2.finish()
+        assert out2 == out and np.array_equal(st2.words, st.words)
+        assert (sp2.reparsed, sp2.collectives) == (0, 1)
+    else:
+        out, st = sp.parse(spec)
     q.put((rank, out, st.words.copy(), eng.n_parses, (sp.reparsed, sp.collectives)))
     dist.barrier()
     dist.destroy_process_group()
@@ -58,7 +70,7 @@ def expect(data: bytes):
     return res, stats_words(150, st, res.n_records)
 
 
-@pytest.mark.parametrize("mode", ["plain", "lie", "nophase"])
+@pytest.mark.parametrize("mode", ["plain", "lie", "nophase", "two_in_flight"])
 def test_two_ranks_match_single_stream(mode, tmp_path):
     data = synth(257)                      # the cut falls inside a record
     res, words = expect(data)
@@ -67,11 +79,11 @@ def test_two_ranks_match_single_stream(mode, tmp_path):
         assert (o.status, o.n_records, o.n_lines) == (0, res.n_records, data.count(b"\n"))
         assert np.array_equal(w, words)
         if rank == 1:
-            assert n_parses == (1 if mode == "plain" else 2), (mode, n_parses)
+            assert n_parses == (1 if mode in ("plain", "two_in_flight") else 2), (mode, n_parses)
         else:
             assert n_parses == 1
         # the common case is ONE collective: the all-reduce of [block | outcome slots] is also the gather
-        assert reparsed[1] == 1 if mode == "plain" else reparsed[1] > 1
+        assert reparsed[1] == 1 if mode in ("plain", "two_in_flight") else reparsed[1] > 1
 
 
 def test_error_in_first_shard_silences_the_second(tmp_path):
