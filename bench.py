@@ -388,7 +388,7 @@ def run_ours(args):
     # kernel alone against the bytes it moves itself (the input).
     achieved = alg_bytes / ((k_ms + i_ms) * 1e-3) / 1e9
     traffic, traffic_src = profiled_traffic(args.gib)
-    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5,32,4096>, HIST, predicting variant> + fq_stream_compact_kernel (index)",
+    roofline = {"bound": "hbm", "kernel": "fq_stream_kernel<SCfg<5,28,4096>, HIST, predicting variant> + fq_stream_compact_kernel (index)",
                 "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": args.traffic_bytes if args.traffic_bytes is not None else traffic,
