@@ -726,35 +726,19 @@ __device__ __forceinline__ uint32_t pred_pass(uint32_t buf_s, const Shape& sh, u
     return first_bad;
 }
 
-// Same for records whose HEADER length varies (instrument coordinates in the id line): lane r holds the
-// window offset of record r and its header length (found by the caller's search for the first '\n' behind the
-// record start, so the header line needs no further check); everything behind the header is predicted from
-// the shape and verified as in pred_pass.  chk_rel: the byte lane i verifies, relative to the sequence line.
+// The rounds for records whose HEADER length varies (instrument coordinates in the id line).  The caller has scanned
+// the window (all its '\n' are in the list) and checked every record against the shape, one lane per record: lane r
+// holds the window offset of the sequence line of record r; nothing is left to verify here.
 template <class C, int NR>
-__device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, uint32_t my_start, uint32_t my_lh,
-                                              uint32_t chk_rel, uint32_t chk_exp, uint32_t chk_neg, uint32_t gm,
-                                              const LaneK& lc, uint32_t hist_s, uint32_t n_rec, uint32_t pass,
-                                              uint32_t sub, uint32_t i, uint32_t kA, uint32_t kB, uint32_t& hib)
+__device__ __forceinline__ uint32_t flex_pass(uint32_t buf_s, const Shape& sh, uint32_t my_body, uint32_t gm, const LaneK& lc,
+                                              uint32_t n_rec, uint32_t pass, uint32_t sub, uint32_t i, uint32_t& hib)
 {
     const uint32_t r = 4u * pass + sub;
-    const bool valid = r < n_rec;
-    const uint32_t from = valid ? r : 0u;
-    const uint32_t s = buf_s + __shfl_sync(0xffffffffu, my_start, from);
-    const uint32_t body = s + __shfl_sync(0xffffffffu, my_lh, from);     // shared address of the sequence line
-    bool lane_ok = ((lds_u8(i == 0u ? s : body + chk_rel) == chk_exp) ? 1u : 0u) != chk_neg;
-    if (sh.Lp > 2u) lane_ok = lane_ok && no_newline32(body, sh.Lsq + 1u, sh.Lsq + sh.Lp - 1u, i, kA, kB);
-    const unsigned nok = __ballot_sync(0xffffffffu, valid && !lane_ok);
-    uint32_t first_bad = NO_START;
-    bool ok = valid;
-    if (nok) {
-        const uint32_t fsub = ((uint32_t)__ffs(nok) - 1u) >> 3;
-        first_bad = 4u * pass + fsub;
-        ok = valid && sub < fsub;
-    }
-    const uint32_t sa = body + 4u * i;
+    const bool ok = r < n_rec;
+    const uint32_t sa = buf_s + __shfl_sync(0xffffffffu, my_body, ok ? r : 0u) + 4u * i;
     const uint32_t qa = sa + sh.Lsq + sh.Lp;
     frounds<C, NR>(sa, qa, ok ? 1u : 0u, ok ? 0x10000u : 0u, ok ? gm : 0u, lc, hib);
-    return first_bad;
+    return NO_START;
 }
 
 // All passes of a predicted window, dispatched once on the number of rounds NR = ceil(n / 32) of its shape
@@ -771,8 +755,7 @@ struct PredWindow {
                                                     hist_s, n_rec, sub, i, kA, kB, hib);
         uint32_t first_bad = NO_START;
         for (uint32_t pass = 0; 4u * pass < n_rec && first_bad == NO_START; ++pass)
-            first_bad = FLEX ? flex_pass<C, NR>(buf_s, sh, my_start, my_lh, chk_off, chk_exp, chk_neg, gm, lc, hist_s, n_rec,
-                                                pass, sub, i, kA, kB, hib)
+            first_bad = FLEX ? flex_pass<C, NR>(buf_s, sh, my_start, gm, lc, n_rec, pass, sub, i, hib)
                              : pred_pass<C, NR>(buf_s, sh, pad, chk_off, chk_exp, chk_neg, gm, lc, hist_s, n_rec, pass, sub,
                                                 i, kA, kB, hib);
         return first_bad;
@@ -1249,68 +1232,58 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) fq_stream_kernel(const __grid_
                     }
                 }
             } else if (HIST && predict && flex && full) {
-                // ---- predicted window, header lengths vary: find every header end ('\n' search over the 128
-                // bytes behind the record start), predict the rest of the record from the shape
-                const uint32_t rest = 2u * sh.Lsq + sh.Lp;
+                // ---- predicted window, header lengths vary: the window is scanned (32 bytes per lane and step, the
+                // scan of the variable-length variant) so that every '\n' is in the list; then one lane per record
+                // checks it against the shape -- the three line lengths behind the header, '@', '+', the '\r' flags --
+                // and the rounds run as for predicted records, from the sequence line the list gives
+                uint32_t hib_unused;
+                const uint32_t total = win_scan<C, false, true>(buf_s, list, w, hib_unused, lane, lt_mask);
+                const uint32_t n_win = min(min(total / 4u, (uint32_t)C::MAXR), 32u);     // complete records looked at
                 const uint32_t lim = room < (unsigned long long)C::WIN ? (uint32_t)room : (uint32_t)C::WIN;
-                uint32_t my_start = 0, my_lh = 0, s = w.pad, n_fit2 = 0;
-                while (n_fit2 < 32u && s < lim) {
-                    const uint32_t a0 = s & ~3u;
-                    uint32_t m = nlbits3(lds32<0>(buf_s + a0 + 4u * (uint32_t)lane), kA, kB);
-                    if (lane == 0) m &= 0xFFFFFFFFu << ((s & 3u) * 8u);          // bytes in front of the record
-                    const unsigned any = __ballot_sync(0xffffffffu, m != 0u);
-                    if (!any) break;                                             // header longer than the search
-                    const uint32_t f = (uint32_t)__ffs(any) - 1u;
-                    const uint32_t mf = __shfl_sync(0xffffffffu, m, f);
-                    const uint32_t lh = a0 + 4u * f + (((uint32_t)__ffs(mf) - 1u) >> 3) + 1u - s;
-                    const uint32_t e = s + lh + rest;
-                    if (e > (uint32_t)C::WIN) break;                             // the record does not fit the window
-                    if ((uint32_t)lane == n_fit2) {
-                        my_start = s;
-                        my_lh = lh;
-                    }
-                    ++n_fit2;
-                    s = e;
+                uint32_t my_body = 0;
+                bool mine = false, good = false;
+                {
+                    const uint32_t j = 4u * min((uint32_t)lane, n_win ? n_win - 1u : 0u);
+                    const uint32_t a = list[j], b = list[j + 1u], c = list[j + 2u], d = list[j + 3u], e = list[j + 4u];
+                    mine = (uint32_t)lane < n_win && a < lim;                            // starts inside the range
+                    good = c - b == sh.Lsq && d - c == sh.Lp && e - d == sh.Lsq && buf[a] == '@' && buf[c] == '+' &&
+                           ((sh.Lsq > 1u && buf[c - 2u] == '\r') ? 1u : 0u) == sh.cr_s &&
+                           ((sh.Lsq > 1u && buf[e - 2u] == '\r') ? 1u : 0u) == sh.cr_q;
+                    my_body = b;
                 }
-                if (n_fit2 == 0) {
-                    predict = false;                                             // scan this window instead
-                    continue;
+                const uint32_t n_in = (uint32_t)__popc(__ballot_sync(0xffffffffu, mine));
+                const unsigned nok = __ballot_sync(0xffffffffu, mine && !good);
+                n_rec = nok ? min(n_in, (uint32_t)__ffs(nok) - 1u) : n_in;
+                if (nok || n_win == 0) {
+                    // the prediction stops holding (or the window holds no complete record): scan next time
+                    predict = false;
+                    if ((n_win == 0 || 2u * n_rec < n_in) && ++strikes >= 2) cooldown = 32;
+                } else {
+                    strikes = 0;
                 }
-                n_rec = n_fit2;
+                if (n_rec == 0) continue;
                 const uint32_t Lr = sh.Lsq - 1u;
                 const uint32_t Ls = Lr - sh.cr_s;
                 uint32_t hib = 0;
-                const uint32_t first_bad = PredWindow<C, true, C::NCHUNK>::run((Ls + 31u) >> 5, buf_s, sh, 0u, my_start, my_lh,
-                                                                               chk_off, chk_exp, chk_neg, gmask, lc, hist_s, n_rec,
-                                                                               sub, li, kA, kB, hib);
+                PredWindow<C, true, C::NCHUNK>::run((Ls + 31u) >> 5, buf_s, sh, 0u, my_body, 0u, 0u, 0u, 0u, gmask, lc, hist_s, n_rec,
+                                                    sub, li, kA, kB, hib);
                 if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {
                     failed = true;
                     break;
                 }
-                if (first_bad != NO_START) {
-                    n_rec = first_bad;
-                    predict = false;
-                    if (2u * first_bad < n_fit2 && ++strikes >= 2) cooldown = 32;
-                } else {
-                    strikes = 0;
-                }
                 ++dbg_pred;
-                if (n_rec == 0) continue;
                 acc_rec += n_rec;    // records of the current shape: counted when it changes or the range ends
                 n_lines = 4u * n_rec;
-                const uint32_t nxt = __shfl_sync(0xffffffffu, my_start, n_rec & 31u);
-                next = n_rec == n_fit2 ? s : nxt;
+                next = list[n_lines];
                 if (want_index) {
                     if (lrank + n_lines > p.stage_share || !desc_put(dout, lane, n_lines, (uint32_t)lrank, 0u)) {
                         failed = true;
                         break;
                     }
+                    const uint32_t off = (uint32_t)(p.stream_offset + w.src) - 1u;       // low 32 bits are what the index holds
                     uint32_t* out = p.index_stage + (size_t)rid * p.stage_share + lrank;
-                    for (uint32_t b = 0; b < n_lines; b += 32u) {
-                        const uint32_t j = b + (uint32_t)lane, r = min(j >> 2, 31u);
-                        const uint32_t v = __shfl_sync(0xffffffffu, my_start, r) + __shfl_sync(0xffffffffu, my_lh, r);
-                        if (j < n_lines) out[j] = (uint32_t)(p.stream_offset + w.src) + v + idx_le;
-                    }
+                    const uint32_t ls = buf_s + (uint32_t)(C::WIN + 16) + 2u;
+                    for (uint32_t j = lane; j < n_lines; j += 32) out[j] = off + lds_u16<0>(ls + 2u * j);
                 }
             } else {
                 // ---- scanned window -------------------------------------------------------------------
