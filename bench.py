@@ -429,6 +429,28 @@ def run_ours(args):
             configs.append(c)
         eng3.close()
         del vbuf, vidx
+        # not a BASELINE configuration, but what sequencers write: fixed 150 bp reads whose id lines vary in length
+        # (tile / x / y coordinates), so no two records start a fixed distance apart
+        rng = np.random.default_rng(7)
+        n_blk = 100000
+        seqs = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n_blk, READ_LEN), dtype=np.uint8)]
+        quals = rng.integers(35, 75, size=(n_blk, READ_LEN), dtype=np.uint8)
+        xs, ys, tiles = rng.integers(1000, 30000, size=n_blk), rng.integers(1000, 100000, size=n_blk), rng.integers(1101, 2678, size=n_blk)
+        parts = []
+        for i in range(n_blk):
+            parts += [b"@A00123:45:HXXXXDSXX:1:%d:%d:%d 1:N:0:ATCACGTT\n" % (tiles[i], xs[i], ys[i]), seqs[i].tobytes(), b"\n+\n",
+                      quals[i].tobytes(), b"\n"]
+        block = np.frombuffer(b"".join(parts), dtype=np.uint8)
+        reps = max(1, int(min(args.gib, 8.0) * GIB) // block.size)
+        n_ill, rec_ill = block.size * reps, n_blk * reps
+        ibuf = torch.zeros(n_ill + 64, dtype=torch.uint8, device=dev)
+        ibuf[:n_ill] = torch.from_numpy(block.copy()).to(dev).repeat(reps)
+        iidx = torch.empty(4 * rec_ill + 8, dtype=torch.int32, device=dev)
+        c = time_config(eng, torch, cs, cw, lambda: eng.parse_device(ibuf, n_own=n_ill, n_avail=n_ill, hist=True, index=iidx),
+                        n_ill, rec_ill, peak, 4 * rec_ill)
+        c["workload"] = f"{n_ill / GIB:.2f} GiB fixed 150 bp with Illumina-like ids of varying length (not a BASELINE configuration), delimit + index + histograms"
+        configs.append(c)
+        del ibuf, iidx
         index = torch.empty(4 * n_rec_upper, dtype=torch.int32, device=dev)
 
     # ---- end to end through the host API (rank-local; pinned host bytes) ---------------------
